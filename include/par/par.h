@@ -1,0 +1,196 @@
+/* par.h — C ABI of the B200-native render path (libpar_b200.so).
+ *
+ * Drop-in boundary for the per-frame hot path of Cons-Cat/Pixel-Art-Raytracer, i.e. the
+ * body of its frame loop, /root/reference/src/alternative.cpp:689-760:
+ *
+ *     memset(count) + count_entities_in_bins(...)      alternative.cpp:690-693, 195-269
+ *     trace_hash_for_pixel(...)                        alternative.cpp:694,     271-383
+ *     shading loop + trace_hash_for_light(...)         alternative.cpp:702-760, 399-500, 40-83
+ *
+ * The reference has no plugin/FFI layer; the seam is that line range.  A host keeps the
+ * reference's own scene types (same layouts, checked by static_asserts below and mirrored
+ * for C++ in par/reference_types.hpp) and replaces the range with
+ *
+ *     par_set_scene(ctx, aabbs, sprite_ids, n);              // upload + device grid build
+ *     par_render(ctx, lights, n_lights, rgba, gbuf, &stats); // primary + shade + readback
+ *
+ * Conventions: every function returns PAR_OK (0) or a negative par_status; no exception
+ * crosses the boundary; par_last_error() gives a thread-local message.  The caller owns all
+ * host buffers and may reuse them as soon as a call returns.  One context serves one host
+ * thread at a time and owns its device memory, stream and events.  There is NO CPU
+ * fallback: without a CUDA device par_create fails with PAR_ERR_NO_DEVICE.
+ */
+#ifndef PAR_PAR_H
+#define PAR_PAR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PAR_BIN_SIZE 40       /* single_bin_cubic_size, alternative.cpp:116 */
+#define PAR_BIN_SLOTS 8       /* sparse_bin_size,       alternative.cpp:131 */
+#define PAR_SPRITE_W 20       /* sprite width hard-coded at alternative.cpp:330 */
+#define PAR_SPRITE_H 40
+#define PAR_SPRITE_TEXELS 800 /* sprites.hpp:68-70 */
+#define PAR_MAX_LIGHTS 64
+#define PAR_MAX_VIEW 12800    /* W, H, L upper bound (one grid-walk step per thread) */
+
+typedef enum par_status {
+    PAR_OK = 0,
+    PAR_ERR_INVALID_ARG = -1,   /* null pointer, bad size, bad band ...              */
+    PAR_ERR_NO_DEVICE = -2,     /* no CUDA device / wrong architecture               */
+    PAR_ERR_CUDA = -3,          /* a CUDA runtime call failed, see par_last_error()  */
+    PAR_ERR_OUT_OF_MEMORY = -4, /* host or device allocation failed                  */
+    PAR_ERR_BAD_SCENE = -5,     /* an AABB would index outside the 20x40 sprite      */
+    PAR_ERR_STATE = -6,         /* call order: atlas and scene must be set first     */
+    PAR_ERR_NCCL = -7           /* multi-GPU gather failed                           */
+} par_status;
+
+/* Reference PODs, byte-identical to the reference's (file:line in comments). */
+typedef struct par_aabb { /* AABB, alternative.cpp:35-38 (alignas 16) */
+    int16_t px, py, pz; /* position */
+    int16_t ex, ey, ez; /* extent   */
+    int16_t pad[2];
+} par_aabb;
+
+typedef struct par_color { /* Color, sprites.hpp:5-6 */
+    uint8_t r, g, b, a;
+} par_color;
+
+typedef struct par_sprite { /* Sprite, sprites.hpp:67-71 */
+    int32_t color[PAR_SPRITE_TEXELS]; /* palette index */
+    int32_t depth[PAR_SPRITE_TEXELS];
+    float normal[PAR_SPRITE_TEXELS][3];
+} par_sprite;
+
+typedef struct par_pixel { /* Pixel, sprites.hpp:53-58 — the G-buffer record */
+    float nx, ny, nz;
+    par_color color;
+    int32_t y, z;
+    int32_t entity;
+} par_pixel;
+
+typedef struct par_light { /* Light, alternative.cpp:619-622 */
+    int16_t x, y, z;
+    int16_t radius; /* never read by the reference */
+} par_light;
+
+/* Replaces the compile-time constants of alternative.cpp:116-131. */
+typedef struct par_config {
+    int32_t width;     /* view_width  (multiple of 40, <= PAR_MAX_VIEW) */
+    int32_t height;    /* view_height (multiple of 40)                  */
+    int32_t length;    /* view_length (multiple of 40)                  */
+    int32_t device;    /* CUDA device ordinal                           */
+    int32_t row_begin; /* this context renders rows [row_begin,row_end); */
+    int32_t row_end;   /* both 0 = the whole frame (row-band multi-GPU)  */
+    float ambient;     /* ambient_light, alternative.cpp:702; 0 selects 0.25f */
+    int32_t reserved[5];
+} par_config;
+
+/* Filled by par_render / par_get_stats; GPU times are CUDA-event milliseconds on the
+ * context's stream for the most recent build / frame. */
+typedef struct par_stats {
+    float ms_grid_build;   /* scene loader kernels (cull + bin + select)        */
+    float ms_primary;      /* ray-gen + intersection kernel                     */
+    float ms_shade;        /* shading + shadow + RGBA8 pack kernel              */
+    float ms_total;        /* first kernel start to last kernel end of the frame */
+    int32_t kernel_launches; /* kernels launched by the most recent build + frame */
+    int32_t n_entities;
+    int32_t n_survivors;   /* entities that passed the cull (alternative.cpp:212-219) */
+    int32_t n_inserts;     /* (entity, bin) insertions (alternative.cpp:243-267)       */
+    uint64_t rays;         /* reference-equivalent rays: rows*W*(1+n_lights)           */
+    uint64_t slab_tests;   /* slab tests actually executed on the device (0 unless the
+                              library was built with PAR_COUNTERS)                      */
+    int32_t reserved[4];
+} par_stats;
+
+typedef struct par_ctx par_ctx;
+
+/* -- lifetime ------------------------------------------------------------------------- */
+int par_create(par_ctx** out, const par_config* cfg);
+void par_destroy(par_ctx* ctx);
+const char* par_last_error(void);
+const char* par_version(void);
+
+/* Use an external CUDA stream (cudaStream_t cast to void*) for all work of this context;
+ * NULL restores the context's own stream.  Lets a host framework order and time the work. */
+int par_set_stream(par_ctx* ctx, void* cuda_stream);
+int par_sync(par_ctx* ctx);
+
+/* Pinned host memory for frame/scene buffers (optional; any host pointer is accepted). */
+void* par_alloc_host(size_t bytes);
+void par_free_host(void* p);
+
+/* -- scene ---------------------------------------------------------------------------- */
+/* Sprite atlas + palette (replaces Entities::sprites, alternative.cpp:95, and color_palette,
+ * sprites.hpp:60-65).  Copied; call once, or again whenever sprites change. */
+int par_set_atlas(par_ctx* ctx, const par_sprite* sprites, int n_sprites,
+                  const par_color* palette, int n_palette);
+
+/* Per-frame scene: replaces Entities::aabbs (alternative.cpp:94) and runs the device scene
+ * loader = memset + count_entities_in_bins (alternative.cpp:690-693).  sprite_ids may be
+ * NULL (every entity uses atlas entry 0, which is what Entities::insert produces,
+ * alternative.cpp:105-108).  Host data is copied before return of the NEXT synchronising
+ * call at the latest when it is pinned; pageable buffers are copied before return. */
+int par_set_scene(par_ctx* ctx, const par_aabb* aabbs, const int32_t* sprite_ids, int n);
+
+/* Re-run the device scene loader on the scene already resident in HBM (no upload). */
+int par_rebuild_grid(par_ctx* ctx);
+
+/* -- frame ---------------------------------------------------------------------------- */
+/* Render one frame and read it back.  out_rgba: host, W*H par_color, caller-owned; rows of
+ * the context's band are written at their place in the full frame (others untouched).
+ * out_gbuf: optional host W*H par_pixel (band rows written).  Synchronous at the API. */
+int par_render(par_ctx* ctx, const par_light* lights, int n_lights, par_color* out_rgba,
+               par_pixel* out_gbuf, par_stats* stats);
+
+/* Render into DEVICE memory, asynchronously on the context's stream: d_rgba points at a
+ * full W*H*4-byte frame in HBM on the context's device; band rows are written in place
+ * (so an in-place all-gather over bands completes the frame).  NULL renders into the
+ * context's own frame buffer.  Use par_sync / stream ordering before consuming it. */
+int par_render_device(par_ctx* ctx, const par_light* lights, int n_lights, void* d_rgba);
+
+/* Device pointer of the context's own W*H*4 frame buffer. */
+void* par_device_frame(par_ctx* ctx);
+
+/* Parity checkpoints of the most recent frame / build (synchronous copies to host):
+ *   gbuf   W*H par_pixel, texel W*H int32 (sprite texel index of the hit, -1 = miss)
+ *   count  int32[volume]  (p_aabb_count_in_bin), ids int32[volume*8] (entity-index map in
+ *          slot order; slots >= count[bin] are -1).  Any pointer may be NULL. */
+int par_get_gbuffer(par_ctx* ctx, par_pixel* gbuf, int32_t* texel);
+int par_get_grid(par_ctx* ctx, int32_t* count, int32_t* ids);
+int par_get_stats(par_ctx* ctx, par_stats* stats);
+int par_grid_volume(const par_ctx* ctx);
+
+/* -- host-side pieces of the reference that sit either side of the path ---------------- */
+/* make_tile_floor(), sprites.hpp:73-364, and color_palette, sprites.hpp:60-65. */
+void par_sprite_tile_floor(par_sprite* out);
+void par_palette_default(par_color out[4]);
+/* Default scene of alternative.cpp:519-599 (scene constants 480/320/320) and its light
+ * (alternative.cpp:624-626).  Returns the entity count; writes at most cap records. */
+int par_scene_default(par_aabb* out, int cap);
+void par_light_default(par_light* out);
+/* SURVEY.md §8(d) synthetic recipe (C3/C5): n cubes + n_lights lights from splitmix64. */
+void par_scene_synthetic(int width, int height, int length, uint64_t seed, int n,
+                         par_aabb* out_aabbs, int n_lights, par_light* out_lights);
+/* Key semantics of alternative.cpp:641-681 on entity 0 / light 0.  key: 'L','R' arrows,
+ * 'U','D' arrows, 'P'/'p' page up/down, and the literal light keys a k j u h o. */
+void par_apply_key(int key, par_aabb* player, par_light* light);
+/* Debug overlay of alternative.cpp:139-175, 762-772 drawn into a host frame. */
+void par_draw_overlay(int width, int height, const par_pixel* gbuf, const par_light* light,
+                      int cursor_x, int cursor_y, par_color* frame);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#if __cplusplus >= 201103L
+static_assert(sizeof(par_aabb) == 16, "AABB must stay 16 bytes (alternative.cpp:88)");
+static_assert(sizeof(par_sprite) == 16000, "Sprite layout (sprites.hpp:67-71)");
+static_assert(sizeof(par_pixel) == 28, "Pixel layout (sprites.hpp:53-58)");
+static_assert(sizeof(par_light) == 8, "Light layout (alternative.cpp:619-622)");
+static_assert(sizeof(par_color) == 4, "Color layout (sprites.hpp:5-6)");
+#endif
+#endif
+#endif /* PAR_PAR_H */

@@ -1,0 +1,530 @@
+// par_api.cu — the extern "C" layer of libpar_b200.so (include/par/par.h): context,
+// device memory, streams/events, and the launch sequence that replaces the reference frame
+// loop body /root/reference/src/alternative.cpp:689-760.  No compute happens on the host and
+// there is no CPU fallback: without a CUDA device every entry point fails.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "par/par.h"
+#include "par_kernels.cuh"
+
+namespace par {
+
+// Expand the compact G-buffer into the reference's Pixel records (sprites.hpp:53-58) and a
+// texel-index plane, for the parity checkpoints of par_get_gbuffer / par_render(out_gbuf).
+__global__ void __launch_bounds__(256)
+k_expand_gbuf(const int4* __restrict__ gbuf, const float* __restrict__ atlas_normal,
+              const unsigned char* __restrict__ atlas_color, const uchar4* __restrict__ palette,
+              size_t first, size_t count, int* __restrict__ out_pixel7, int* __restrict__ out_texel) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    size_t px = first + t;
+    int4 g = gbuf[px];
+    float nx = 0.f, ny = 0.f, nz = 0.f;
+    uchar4 c = make_uchar4(127, 127, 127, 0);  // alternative.cpp:281
+    int texel = -1;
+    if (g.w >= 0) {
+        int spr = g.w >> 10;
+        texel = g.w & 1023;
+        const float* nrm = atlas_normal + (spr * kTexels + texel) * 3;
+        nx = nrm[0];
+        ny = nrm[1];
+        nz = nrm[2];
+        c = palette[atlas_color[spr * kTexels + texel]];
+    }
+    if (out_pixel7) {
+        int* o = out_pixel7 + px * 7;
+        o[0] = __float_as_int(nx);
+        o[1] = __float_as_int(ny);
+        o[2] = __float_as_int(nz);
+        o[3] = (int)((unsigned)c.x | (unsigned)c.y << 8 | (unsigned)c.z << 16 | (unsigned)c.w << 24);
+        o[4] = g.y;
+        o[5] = g.z;
+        o[6] = g.x;
+    }
+    if (out_texel) out_texel[px] = texel;
+}
+
+}  // namespace par
+
+using namespace par;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, const char* a = "", const char* b = "") {
+    snprintf(g_err, sizeof g_err, fmt, a, b);
+    return code;
+}
+
+#define PAR_CUDA(call)                                                                   \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess)                                                           \
+            return fail(e_ == cudaErrorMemoryAllocation ? PAR_ERR_OUT_OF_MEMORY : PAR_ERR_CUDA, \
+                        "%s: %s", #call, cudaGetErrorString(e_));                        \
+    } while (0)
+
+struct par_ctx {
+    par_config cfg;
+    ViewDims d;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev_build0 = nullptr, ev_build1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr,
+                ev_f2 = nullptr;
+    // scene
+    int4* d_raw = nullptr;
+    int4* d_boxes = nullptr;
+    int* d_sprite_ids = nullptr;
+    int* d_survivors = nullptr;
+    int cap_entities = 0, n_entities = 0;
+    bool has_sprite_ids = false;
+    // grid
+    int* d_cnt = nullptr;
+    int* d_ids = nullptr;
+    LoaderCounters* d_ctr = nullptr;
+    LoaderCounters* h_ctr = nullptr;  // pinned
+    // atlas
+    int* d_atlas_depth = nullptr;
+    float* d_atlas_normal = nullptr;
+    unsigned char* d_atlas_color = nullptr;
+    uchar4* d_palette = nullptr;
+    int n_sprites = 0, n_palette = 0;
+    // frame
+    int4* d_gbuf = nullptr;
+    uchar4* d_frame = nullptr;
+    int* d_expanded = nullptr;  // W*H*7 ints, lazily allocated
+    int* d_texel = nullptr;     // W*H ints, lazily allocated
+    bool scene_set = false, frame_valid = false, build_timed = false, frame_timed = false;
+    int launches_build = 0, launches_frame = 0, last_n_lights = 0;
+    float ambient = 0.25f;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (prev >= 0 && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+int run_loader(par_ctx* c) {
+    c->launches_build = 0;
+    PAR_CUDA(cudaEventRecord(c->ev_build0, c->stream));
+    PAR_CUDA(launch_scene_loader(c->d_raw, c->has_sprite_ids ? c->d_sprite_ids : nullptr,
+                                 c->n_entities, c->n_sprites, c->d, c->d_boxes, c->d_cnt, c->d_ids,
+                                 c->d_survivors, c->d_ctr, c->stream, &c->launches_build));
+    PAR_CUDA(cudaEventRecord(c->ev_build1, c->stream));
+    PAR_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(LoaderCounters), cudaMemcpyDeviceToHost,
+                             c->stream));
+    c->build_timed = true;
+    c->scene_set = true;
+    c->frame_valid = false;
+    return PAR_OK;
+}
+
+int check_scene_flag(par_ctx* c) {
+    if (c->h_ctr->bad_scene)
+        return fail(PAR_ERR_BAD_SCENE,
+                    "scene has an AABB with extent.x outside [0,20], extent.y+extent.z outside "
+                    "[0,40] or a sprite id outside the atlas (would index outside the 20x40 "
+                    "sprite, alternative.cpp:330)%s%s");
+    return PAR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* par_last_error(void) { return g_err; }
+const char* par_version(void) { return "par_b200 0.1 (sm_100a)"; }
+
+int par_create(par_ctx** out, const par_config* cfg) {
+    if (!out || !cfg) return fail(PAR_ERR_INVALID_ARG, "par_create: null argument%s%s");
+    *out = nullptr;
+    const int B = kBin;
+    if (cfg->width <= 0 || cfg->height <= 0 || cfg->length <= 0 || cfg->width % B ||
+        cfg->height % B || cfg->length % B || cfg->width > PAR_MAX_VIEW ||
+        cfg->height > PAR_MAX_VIEW || cfg->length > PAR_MAX_VIEW)
+        return fail(PAR_ERR_INVALID_ARG,
+                    "par_create: width/height/length must be positive multiples of 40 and <= 12800%s%s");
+    int row0 = cfg->row_begin, row1 = cfg->row_end;
+    if (row0 == 0 && row1 == 0) row1 = cfg->height;
+    if (row0 < 0 || row1 > cfg->height || row0 >= row1)
+        return fail(PAR_ERR_INVALID_ARG, "par_create: bad row band%s%s");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(PAR_ERR_NO_DEVICE, "par_create: no CUDA device (this library has no CPU fallback)%s%s");
+    }
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(PAR_ERR_INVALID_ARG, "par_create: device ordinal out of range%s%s");
+    cudaDeviceProp prop;
+    PAR_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(PAR_ERR_NO_DEVICE, "par_create: device %s is not sm_100 (kernels are built for sm_100a only)%s",
+                    prop.name);
+
+    par_ctx* c = new (std::nothrow) par_ctx;
+    if (!c) return fail(PAR_ERR_OUT_OF_MEMORY, "par_create: host allocation failed%s%s");
+    c->cfg = *cfg;
+    c->ambient = cfg->ambient == 0.f ? 0.25f : cfg->ambient;
+    ViewDims& d = c->d;
+    d.W = cfg->width;
+    d.H = cfg->height;
+    d.L = cfg->length;
+    d.HW = d.W / B;
+    d.HH = d.H / B;
+    d.HL = d.L / B;
+    d.V = d.HW * d.HH * d.HL;
+    d.row0 = row0;
+    d.row1 = row1;
+
+    DeviceGuard guard(cfg->device);
+    int rc = [&]() -> int {
+        PAR_CUDA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+        c->stream = c->own_stream;
+        PAR_CUDA(cudaEventCreate(&c->ev_build0));
+        PAR_CUDA(cudaEventCreate(&c->ev_build1));
+        PAR_CUDA(cudaEventCreate(&c->ev_f0));
+        PAR_CUDA(cudaEventCreate(&c->ev_f1));
+        PAR_CUDA(cudaEventCreate(&c->ev_f2));
+        size_t px = (size_t)d.W * d.H;
+        PAR_CUDA(cudaMalloc(&c->d_cnt, sizeof(int) * (size_t)d.V));
+        PAR_CUDA(cudaMalloc(&c->d_ids, sizeof(int) * (size_t)d.V * kSlots));
+        PAR_CUDA(cudaMalloc(&c->d_ctr, sizeof(LoaderCounters)));
+        PAR_CUDA(cudaMallocHost(&c->h_ctr, sizeof(LoaderCounters)));
+        memset(c->h_ctr, 0, sizeof(LoaderCounters));
+        PAR_CUDA(cudaMalloc(&c->d_gbuf, sizeof(int4) * px));
+        PAR_CUDA(cudaMalloc(&c->d_frame, sizeof(uchar4) * px));
+        PAR_CUDA(cudaMemsetAsync(c->d_frame, 0, sizeof(uchar4) * px, c->stream));
+        PAR_CUDA(cudaMemsetAsync(c->d_gbuf, 0, sizeof(int4) * px, c->stream));
+        PAR_CUDA(configure_primary(primary_smem_bytes(d, 1)));
+        return PAR_OK;
+    }();
+    if (rc != PAR_OK) {
+        par_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return PAR_OK;
+}
+
+void par_destroy(par_ctx* c) {
+    if (!c) return;
+    DeviceGuard guard(c->cfg.device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    cudaFree(c->d_raw);
+    cudaFree(c->d_boxes);
+    cudaFree(c->d_sprite_ids);
+    cudaFree(c->d_survivors);
+    cudaFree(c->d_cnt);
+    cudaFree(c->d_ids);
+    cudaFree(c->d_ctr);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    cudaFree(c->d_atlas_depth);
+    cudaFree(c->d_atlas_normal);
+    cudaFree(c->d_atlas_color);
+    cudaFree(c->d_palette);
+    cudaFree(c->d_gbuf);
+    cudaFree(c->d_frame);
+    cudaFree(c->d_expanded);
+    cudaFree(c->d_texel);
+    cudaEvent_t evs[] = {c->ev_build0, c->ev_build1, c->ev_f0, c->ev_f1, c->ev_f2};
+    for (cudaEvent_t e : evs)
+        if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+}
+
+int par_set_stream(par_ctx* c, void* cuda_stream) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_set_stream: null context%s%s");
+    DeviceGuard guard(c->cfg.device);
+    PAR_CUDA(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return PAR_OK;
+}
+
+int par_sync(par_ctx* c) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_sync: null context%s%s");
+    DeviceGuard guard(c->cfg.device);
+    PAR_CUDA(cudaStreamSynchronize(c->stream));
+    return c->scene_set ? check_scene_flag(c) : PAR_OK;
+}
+
+void* par_alloc_host(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        fail(PAR_ERR_OUT_OF_MEMORY, "par_alloc_host: cudaMallocHost failed%s%s");
+        return nullptr;
+    }
+    return p;
+}
+
+void par_free_host(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int par_set_atlas(par_ctx* c, const par_sprite* sprites, int n_sprites, const par_color* palette,
+                  int n_palette) {
+    if (!c || !sprites || !palette || n_sprites <= 0 || n_palette <= 0 || n_palette > 256 ||
+        n_sprites > (1 << 20))
+        return fail(PAR_ERR_INVALID_ARG, "par_set_atlas: bad argument%s%s");
+    // Compact atlas: the 16000-byte reference Sprite becomes three dense tables.
+    size_t nt = (size_t)n_sprites * kTexels;
+    int* depth = (int*)malloc(nt * sizeof(int));
+    float* normal = (float*)malloc(nt * 3 * sizeof(float));
+    unsigned char* color = (unsigned char*)malloc(nt);
+    if (!depth || !normal || !color) {
+        free(depth);
+        free(normal);
+        free(color);
+        return fail(PAR_ERR_OUT_OF_MEMORY, "par_set_atlas: host allocation failed%s%s");
+    }
+    bool ok = true;
+    for (int s = 0; s < n_sprites && ok; s++)
+        for (int t = 0; t < kTexels; t++) {
+            int ci = sprites[s].color[t];
+            if (ci < 0 || ci >= n_palette) {
+                ok = false;
+                break;
+            }
+            color[(size_t)s * kTexels + t] = (unsigned char)ci;
+            depth[(size_t)s * kTexels + t] = sprites[s].depth[t];
+            memcpy(&normal[((size_t)s * kTexels + t) * 3], sprites[s].normal[t], 3 * sizeof(float));
+        }
+    int rc = PAR_OK;
+    if (!ok) {
+        rc = fail(PAR_ERR_INVALID_ARG, "par_set_atlas: sprite colour index outside the palette%s%s");
+    } else {
+        DeviceGuard guard(c->cfg.device);
+        rc = [&]() -> int {
+            PAR_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_atlas_depth);
+            cudaFree(c->d_atlas_normal);
+            cudaFree(c->d_atlas_color);
+            cudaFree(c->d_palette);
+            c->d_atlas_depth = nullptr;
+            c->d_atlas_normal = nullptr;
+            c->d_atlas_color = nullptr;
+            c->d_palette = nullptr;
+            c->n_sprites = 0;
+            PAR_CUDA(cudaMalloc(&c->d_atlas_depth, nt * sizeof(int)));
+            PAR_CUDA(cudaMalloc(&c->d_atlas_normal, nt * 3 * sizeof(float)));
+            PAR_CUDA(cudaMalloc(&c->d_atlas_color, nt));
+            PAR_CUDA(cudaMalloc(&c->d_palette, sizeof(uchar4) * 256));
+            PAR_CUDA(cudaMemcpy(c->d_atlas_depth, depth, nt * sizeof(int), cudaMemcpyHostToDevice));
+            PAR_CUDA(cudaMemcpy(c->d_atlas_normal, normal, nt * 3 * sizeof(float), cudaMemcpyHostToDevice));
+            PAR_CUDA(cudaMemcpy(c->d_atlas_color, color, nt, cudaMemcpyHostToDevice));
+            PAR_CUDA(cudaMemset(c->d_palette, 0, sizeof(uchar4) * 256));
+            PAR_CUDA(cudaMemcpy(c->d_palette, palette, sizeof(par_color) * n_palette, cudaMemcpyHostToDevice));
+            PAR_CUDA(configure_primary(primary_smem_bytes(c->d, n_sprites)));
+            c->n_sprites = n_sprites;
+            c->n_palette = n_palette;
+            c->frame_valid = false;
+            return PAR_OK;
+        }();
+    }
+    free(depth);
+    free(normal);
+    free(color);
+    return rc;
+}
+
+int par_set_scene(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n) {
+    if (!c || n < 0 || (n > 0 && !aabbs))
+        return fail(PAR_ERR_INVALID_ARG, "par_set_scene: bad argument%s%s");
+    if (c->n_sprites == 0) return fail(PAR_ERR_STATE, "par_set_scene: call par_set_atlas first%s%s");
+    DeviceGuard guard(c->cfg.device);
+    if (n > c->cap_entities) {
+        PAR_CUDA(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_raw);
+        cudaFree(c->d_boxes);
+        cudaFree(c->d_sprite_ids);
+        cudaFree(c->d_survivors);
+        c->d_raw = c->d_boxes = nullptr;
+        c->d_sprite_ids = c->d_survivors = nullptr;
+        c->cap_entities = 0;
+        size_t cap = (size_t)n + (size_t)n / 8 + 64;
+        PAR_CUDA(cudaMalloc(&c->d_raw, sizeof(int4) * cap));
+        PAR_CUDA(cudaMalloc(&c->d_boxes, sizeof(int4) * cap));
+        PAR_CUDA(cudaMalloc(&c->d_sprite_ids, sizeof(int) * cap));
+        PAR_CUDA(cudaMalloc(&c->d_survivors, sizeof(int) * cap));
+        c->cap_entities = (int)cap;
+    }
+    c->n_entities = n;
+    c->has_sprite_ids = sprite_ids != nullptr;
+    if (n > 0) {
+        PAR_CUDA(cudaMemcpyAsync(c->d_raw, aabbs, sizeof(par_aabb) * (size_t)n, cudaMemcpyHostToDevice,
+                                 c->stream));
+        if (sprite_ids)
+            PAR_CUDA(cudaMemcpyAsync(c->d_sprite_ids, sprite_ids, sizeof(int) * (size_t)n,
+                                     cudaMemcpyHostToDevice, c->stream));
+    }
+    return run_loader(c);
+}
+
+int par_rebuild_grid(par_ctx* c) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_rebuild_grid: null context%s%s");
+    if (!c->scene_set) return fail(PAR_ERR_STATE, "par_rebuild_grid: no scene resident%s%s");
+    DeviceGuard guard(c->cfg.device);
+    return run_loader(c);
+}
+
+int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d_rgba) {
+    if (!c || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
+        return fail(PAR_ERR_INVALID_ARG, "par_render_device: bad argument (at most 64 lights)%s%s");
+    if (!c->scene_set || c->n_sprites == 0)
+        return fail(PAR_ERR_STATE, "par_render_device: set the atlas and the scene first%s%s");
+    DeviceGuard guard(c->cfg.device);
+    const ViewDims& d = c->d;
+    PrimaryParams pp;
+    pp.d = d;
+    pp.cnt = c->d_cnt;
+    pp.ids = c->d_ids;
+    pp.boxes = c->d_boxes;
+    pp.atlas_depth = c->d_atlas_depth;
+    pp.n_sprites = c->n_sprites;
+    pp.gbuf = c->d_gbuf;
+    pp.tile_row_first = d.row0 / kBin;
+    ShadeParams sp;
+    sp.d = d;
+    sp.cnt = c->d_cnt;
+    sp.ids = c->d_ids;
+    sp.boxes = c->d_boxes;
+    sp.gbuf = c->d_gbuf;
+    sp.atlas_normal = c->d_atlas_normal;
+    sp.atlas_color = c->d_atlas_color;
+    sp.palette = c->d_palette;
+    sp.out = d_rgba ? static_cast<uchar4*>(d_rgba) : c->d_frame;
+    sp.n_lights = n_lights;
+    sp.ambient = c->ambient;
+    sp.tile_row_first = d.row0 / kBin;
+    sp.slab_counter = nullptr;
+    memset(sp.lights, 0, sizeof sp.lights);
+    for (int l = 0; l < n_lights; l++)
+        sp.lights[l] = make_short4(lights[l].x, lights[l].y, lights[l].z, lights[l].radius);
+    PAR_CUDA(cudaEventRecord(c->ev_f0, c->stream));
+    PAR_CUDA(launch_primary(pp, c->stream));
+    PAR_CUDA(cudaEventRecord(c->ev_f1, c->stream));
+    PAR_CUDA(launch_shade(sp, c->stream));
+    PAR_CUDA(cudaEventRecord(c->ev_f2, c->stream));
+    c->launches_frame = 2;
+    c->last_n_lights = n_lights;
+    c->frame_valid = true;
+    c->frame_timed = true;
+    return PAR_OK;
+}
+
+void* par_device_frame(par_ctx* c) { return c ? c->d_frame : nullptr; }
+
+static int expand_gbuffer(par_ctx* c, par_pixel* gbuf, int32_t* texel) {
+    const ViewDims& d = c->d;
+    size_t px = (size_t)d.W * d.H;
+    size_t first = (size_t)d.row0 * d.W, count = (size_t)(d.row1 - d.row0) * d.W;
+    if (gbuf && !c->d_expanded) PAR_CUDA(cudaMalloc(&c->d_expanded, sizeof(int) * 7 * px));
+    if (texel && !c->d_texel) PAR_CUDA(cudaMalloc(&c->d_texel, sizeof(int) * px));
+    k_expand_gbuf<<<(unsigned)((count + 255) / 256), 256, 0, c->stream>>>(
+        c->d_gbuf, c->d_atlas_normal, c->d_atlas_color, c->d_palette, first, count,
+        gbuf ? c->d_expanded : nullptr, texel ? c->d_texel : nullptr);
+    PAR_CUDA(cudaGetLastError());
+    if (gbuf)
+        PAR_CUDA(cudaMemcpyAsync(gbuf + first, c->d_expanded + first * 7, sizeof(par_pixel) * count,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    if (texel)
+        PAR_CUDA(cudaMemcpyAsync(texel + first, c->d_texel + first, sizeof(int) * count,
+                                 cudaMemcpyDeviceToHost, c->stream));
+    return PAR_OK;
+}
+
+int par_get_stats(par_ctx* c, par_stats* st) {
+    if (!c || !st) return fail(PAR_ERR_INVALID_ARG, "par_get_stats: null argument%s%s");
+    DeviceGuard guard(c->cfg.device);
+    PAR_CUDA(cudaStreamSynchronize(c->stream));
+    memset(st, 0, sizeof *st);
+    if (c->build_timed) PAR_CUDA(cudaEventElapsedTime(&st->ms_grid_build, c->ev_build0, c->ev_build1));
+    if (c->frame_timed) {
+        PAR_CUDA(cudaEventElapsedTime(&st->ms_primary, c->ev_f0, c->ev_f1));
+        PAR_CUDA(cudaEventElapsedTime(&st->ms_shade, c->ev_f1, c->ev_f2));
+        PAR_CUDA(cudaEventElapsedTime(&st->ms_total, c->ev_f0, c->ev_f2));
+    }
+    st->kernel_launches = c->launches_build + c->launches_frame;
+    st->n_entities = c->n_entities;
+    st->n_survivors = c->h_ctr->n_survivors;
+    st->n_inserts = c->h_ctr->n_inserts;
+    st->rays = (uint64_t)(c->d.row1 - c->d.row0) * c->d.W * (1 + (uint64_t)c->last_n_lights);
+    return PAR_OK;
+}
+
+int par_render(par_ctx* c, const par_light* lights, int n_lights, par_color* out_rgba,
+               par_pixel* out_gbuf, par_stats* stats) {
+    if (!c || !out_rgba) return fail(PAR_ERR_INVALID_ARG, "par_render: null argument%s%s");
+    int rc = par_render_device(c, lights, n_lights, nullptr);
+    if (rc != PAR_OK) return rc;
+    DeviceGuard guard(c->cfg.device);
+    const ViewDims& d = c->d;
+    size_t first = (size_t)d.row0 * d.W, count = (size_t)(d.row1 - d.row0) * d.W;
+    PAR_CUDA(cudaMemcpyAsync(out_rgba + first, c->d_frame + first, sizeof(par_color) * count,
+                             cudaMemcpyDeviceToHost, c->stream));
+    if (out_gbuf && (rc = expand_gbuffer(c, out_gbuf, nullptr)) != PAR_OK) return rc;
+    PAR_CUDA(cudaStreamSynchronize(c->stream));
+    if ((rc = check_scene_flag(c)) != PAR_OK) return rc;
+    if (stats) return par_get_stats(c, stats);
+    return PAR_OK;
+}
+
+int par_get_gbuffer(par_ctx* c, par_pixel* gbuf, int32_t* texel) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_get_gbuffer: null context%s%s");
+    if (!c->frame_valid) return fail(PAR_ERR_STATE, "par_get_gbuffer: no frame rendered%s%s");
+    DeviceGuard guard(c->cfg.device);
+    int rc = expand_gbuffer(c, gbuf, texel);
+    if (rc != PAR_OK) return rc;
+    PAR_CUDA(cudaStreamSynchronize(c->stream));
+    return PAR_OK;
+}
+
+int par_grid_volume(const par_ctx* c) { return c ? c->d.V : 0; }
+
+int par_get_grid(par_ctx* c, int32_t* count, int32_t* ids) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_get_grid: null context%s%s");
+    if (!c->scene_set) return fail(PAR_ERR_STATE, "par_get_grid: no scene resident%s%s");
+    DeviceGuard guard(c->cfg.device);
+    size_t V = (size_t)c->d.V;
+    int* cnt = (int*)malloc(sizeof(int) * V);
+    if (!cnt) return fail(PAR_ERR_OUT_OF_MEMORY, "par_get_grid: host allocation failed%s%s");
+    cudaError_t e = cudaMemcpyAsync(cnt, c->d_cnt, sizeof(int) * V, cudaMemcpyDeviceToHost, c->stream);
+    if (!e && ids)
+        e = cudaMemcpyAsync(ids, c->d_ids, sizeof(int) * V * kSlots, cudaMemcpyDeviceToHost, c->stream);
+    if (!e) e = cudaStreamSynchronize(c->stream);
+    if (e) {
+        free(cnt);
+        return fail(PAR_ERR_CUDA, "par_get_grid: %s%s", cudaGetErrorString(e));
+    }
+    // Layout conversion only: device keeps insert totals and descending winners; the
+    // reference's view is count = total & 7 and slots in ascending entity order (quirk Q2).
+    for (size_t f = 0; f < V; f++) {
+        int keep = cnt[f] & (kSlots - 1);
+        if (ids) {
+            int* row = ids + f * kSlots;
+            for (int a = 0, b = keep - 1; a < b; a++, b--) {
+                int t = row[a];
+                row[a] = row[b];
+                row[b] = t;
+            }
+            for (int s = keep; s < kSlots; s++) row[s] = -1;
+        }
+        if (count) count[f] = keep;
+    }
+    free(cnt);
+    return check_scene_flag(c);
+}
+
+}  // extern "C"

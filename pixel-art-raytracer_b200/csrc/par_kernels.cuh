@@ -1,0 +1,55 @@
+// par_kernels.cuh — parameter blocks and host-side launchers of the three kernel groups
+// (scene_loader.cu, primary.cu, shade.cu); shared with the C ABI layer (par_api.cu).
+#pragma once
+#include "par_device.cuh"
+
+namespace par {
+
+// ---- scene loader (alternative.cpp:690-693, 195-269) ----
+struct LoaderCounters {
+    int n_survivors;
+    int n_inserts;
+    int max_inserts_per_bin;
+    int bad_scene;  // set when an AABB would index outside the 20x40 sprite (quirk Q7)
+};
+cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,
+                                const ViewDims& d, int4* boxes, int* cnt, int* ids,
+                                int* survivors, LoaderCounters* ctr, cudaStream_t s,
+                                int* launches);
+
+// ---- primary rays (alternative.cpp:271-383) ----
+struct PrimaryParams {
+    ViewDims d;
+    const int* cnt;
+    const int* ids;
+    const int4* boxes;
+    const int* atlas_depth;  // [n_sprites][800]
+    int n_sprites;
+    int4* gbuf;
+    int tile_row_first;  // first tile row (bin_y) of the band
+};
+size_t primary_smem_bytes(const ViewDims& d, int n_sprites);
+cudaError_t configure_primary(size_t smem);  // per device, before the first launch
+cudaError_t launch_primary(const PrimaryParams& p, cudaStream_t s);
+
+// ---- shading + shadow rays + RGBA8 pack (alternative.cpp:702-760, 399-500, 40-83) ----
+constexpr int kMaxLights = 64;
+struct ShadeParams {
+    ViewDims d;
+    const int* cnt;
+    const int* ids;
+    const int4* boxes;
+    const int4* gbuf;
+    const float* atlas_normal;         // [n_sprites][800][3]
+    const unsigned char* atlas_color;  // [n_sprites][800] palette index
+    const uchar4* palette;
+    uchar4* out;  // full frame, W*H
+    int n_lights;
+    float ambient;
+    int tile_row_first;
+    unsigned long long* slab_counter;  // optional instrumentation (NULL in production)
+    short4 lights[kMaxLights];         // x, y, z, radius (alternative.cpp:619-622)
+};
+cudaError_t launch_shade(const ShadeParams& p, cudaStream_t s);
+
+}  // namespace par

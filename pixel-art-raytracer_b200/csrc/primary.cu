@@ -1,0 +1,143 @@
+// primary.cu — ray generation + ray-sprite intersection + nearest-hit selection:
+// replaces trace_hash_for_pixel (/root/reference/src/alternative.cpp:271-383).
+//
+// Every primary ray has slope <0,-1,+1> and stays in one column of bins (pixel x / 40,
+// pixel row / 40) while bin_z runs near to far (alternative.cpp:287-296).  One CTA owns one
+// 40x40 screen tile = one bin column:
+//   1. stage the column: per-bin counts -> exclusive scan -> the column's entries (in the
+//      reference's bin_z-then-slot order) are gathered into shared memory ONCE per tile,
+//      pre-digested into the integers the per-pixel test needs;
+//   2. one thread per pixel (40 columns x 8 rows per pass, 5 passes) walks that list: 2-D
+//      integer hit test (quirk Q6), texel index (Q7), depth key with strict-greater select
+//      (Q8), two-adjacent-bins early-out (Q9), miss pixel (Q10), G-buffer record (Q11).
+// Integer only; output is the compact G-buffer (par_device.cuh).
+#include <climits>
+
+#include "par_kernels.cuh"
+
+namespace par {
+
+constexpr int kStagedSprites = 4;  // depth tables staged in shared memory when the atlas is this small
+
+// Dynamic shared memory layout: int s_cnt[HL], int s_off[HL+1], int4 A[n], int4 B[n], int2 C[n]
+// with n <= 7*HL, then (optionally) the depth tables.
+__global__ void __launch_bounds__(kTileThreads)
+k_primary(PrimaryParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const ViewDims& d = p.d;
+    const int max_entries = (kSlots - 1) * d.HL;
+    int4* sA = reinterpret_cast<int4*>(smem_raw);  // x0, x1 (exclusive), lo = py+pz, top = py+ey+pz+ez
+    int4* sB = sA + max_entries;                   // key0 = py-pz, ey, pz, ybase = py+ey+ez
+    int2* sC = reinterpret_cast<int2*>(sB + max_entries);  // entity, sprite<<2 | gap<<1 | first
+    int* s_cnt = reinterpret_cast<int*>(sC + max_entries);
+    int* s_off = s_cnt + d.HL;
+    int* s_depth = s_off + d.HL + 1;
+    const bool staged = p.n_sprites <= kStagedSprites;
+
+    const int tid = threadIdx.x;
+    const int bx = blockIdx.x % d.HW;
+    const int ty = p.tile_row_first + blockIdx.x / d.HW;
+
+    // 1a. counts of the column (the reference's wrapping count is cnt & 7)
+    for (int bz = tid; bz < d.HL; bz += blockDim.x)
+        s_cnt[bz] = p.cnt[flat_bin(d, bx, ty, bz)] & (kSlots - 1);
+    if (staged)
+        for (int i = tid; i < p.n_sprites * kTexels; i += blockDim.x) s_depth[i] = p.atlas_depth[i];
+    __syncthreads();
+    // 1b. exclusive scan over bin_z by warp 0
+    if (tid < 32) {
+        int carry = 0;
+        for (int base = 0; base < d.HL; base += 32) {
+            int bz = base + tid;
+            int v = bz < d.HL ? s_cnt[bz] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (tid >= o) incl += t;
+            }
+            if (bz < d.HL) s_off[bz] = carry + incl - v;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (tid == 0) s_off[d.HL] = carry;
+    }
+    __syncthreads();
+    // 1c. gather entries in (bin_z ascending, slot ascending) order
+    for (int i = tid; i < d.HL * kSlots; i += blockDim.x) {
+        int bz = i >> 3, s = i & 7, c = s_cnt[bz];
+        if (s >= c) continue;
+        int f = flat_bin(d, bx, ty, bz);
+        int ent = p.ids[f * kSlots + (c - 1 - s)];
+        Box b = unpack_box(p.boxes[ent]);
+        int pos = s_off[bz] + s;
+        sA[pos] = make_int4(b.px, b.px + b.ex, b.py + b.pz, b.py + b.ey + b.pz + b.ez);
+        sB[pos] = make_int4(b.py - b.pz, b.ey, b.pz, b.py + b.ey + b.ez);
+        int first = (s == 0);
+        int gap = first && (bz == 0 || s_cnt[bz - 1] == 0);  // an empty bin precedes this one
+        sC[pos] = make_int2(ent, b.sprite << 2 | gap << 1 | first);
+    }
+    __syncthreads();
+    const int n = s_off[d.HL];
+
+    // 2. per-pixel walk
+    const int col = tid % kBin, rsub = tid / kBin;
+    const int i = bx * kBin + col;
+    const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
+#pragma unroll 1
+    for (int m = 0; m < kTileRowsPerThread; m++) {
+        const int j = ty * kBin + rsub + 8 * m;
+        if (j < ra || j >= rb) continue;
+        const int wj = (short)(d.H - j);  // world_j, alternative.cpp:280
+        int best = INT_MIN;               // closest_entity_depth, alternative.cpp:289
+        int run = 0, any = 0;             // intersected_bin_count / has_intersected
+        int4 out = make_int4(0, 0, 0, -1);  // miss: entity 0, y 0, z 0 (quirk Q10)
+        for (int k = 0; k < n; k++) {
+            const int2 c = sC[k];
+            if (c.y & 1) {  // first entry of a bin: close the previous bin (alternative.cpp:368-374)
+                run += any;
+                any = 0;
+                if (run >= 2) break;
+                if (c.y & 2) run = 0;  // an empty bin in between resets the run (alternative.cpp:298-300)
+            }
+            const int4 a = sA[k];
+            if (i >= a.x && i < a.y && wj > a.z && wj <= a.w) {  // quirk Q6
+                const int4 b = sB[k];
+                const int spr = c.y >> 2;
+                const int row = a.w - wj;
+                const int idx = row * kSpriteW + (i - a.x);  // quirk Q7
+                const int dep = staged ? s_depth[spr * kTexels + idx]
+                                       : __ldg(&p.atlas_depth[spr * kTexels + idx]);
+                const int key = b.x + min(0, b.y - row) - dep;  // quirk Q8
+                if (best < key) {  // strict: ties keep the earlier (bin_z, slot)
+                    best = key;
+                    out = make_int4(c.x, b.w - row - dep, b.z + dep, idx | spr << 10);  // Q11
+                    any = 1;
+                }
+            }
+        }
+        p.gbuf[(size_t)j * d.W + i] = out;
+    }
+}
+
+size_t primary_smem_bytes(const ViewDims& d, int n_sprites) {
+    size_t n = (size_t)(kSlots - 1) * d.HL;
+    size_t bytes = n * (16 + 16 + 8) + sizeof(int) * (2 * (size_t)d.HL + 1);
+    if (n_sprites <= kStagedSprites) bytes += sizeof(int) * (size_t)n_sprites * kTexels;
+    return bytes;
+}
+
+cudaError_t configure_primary(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(k_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t launch_primary(const PrimaryParams& p, cudaStream_t s) {
+    const ViewDims& d = p.d;
+    int tile_rows = (d.row1 + kBin - 1) / kBin - d.row0 / kBin;
+    if (tile_rows <= 0) return cudaSuccess;
+    size_t smem = primary_smem_bytes(d, p.n_sprites);
+    k_primary<<<tile_rows * d.HW, kTileThreads, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace par

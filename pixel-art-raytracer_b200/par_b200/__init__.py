@@ -1,0 +1,273 @@
+"""par_b200 — thin ctypes binding of libpar_b200.so (include/par/par.h).
+
+The library is the product: hand-written sm_100a CUDA kernels behind a C ABI that replaces
+the frame-loop body of Cons-Cat/Pixel-Art-Raytracer (/root/reference/src/alternative.cpp:689-760).
+This module only marshals numpy arrays whose dtypes mirror the reference PODs.  There is no
+CPU fallback: importing works anywhere (so symbols can be checked), but creating a Renderer
+without the built library or without a B200 raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpar_b200.so")
+
+# numpy mirrors of the reference PODs (alternative.cpp:35-38, 619-622; sprites.hpp:5-6, 53-58, 67-71)
+AABB = np.dtype([("px", "<i2"), ("py", "<i2"), ("pz", "<i2"), ("ex", "<i2"), ("ey", "<i2"),
+                 ("ez", "<i2"), ("pad", "<i2", (2,))])
+COLOR = np.dtype([("r", "u1"), ("g", "u1"), ("b", "u1"), ("a", "u1")])
+PIXEL = np.dtype([("nx", "<f4"), ("ny", "<f4"), ("nz", "<f4"), ("color", COLOR), ("y", "<i4"),
+                  ("z", "<i4"), ("entity", "<i4")])
+LIGHT = np.dtype([("x", "<i2"), ("y", "<i2"), ("z", "<i2"), ("radius", "<i2")])
+SPRITE = np.dtype([("color", "<i4", (800,)), ("depth", "<i4", (800,)),
+                   ("normal", "<f4", (800, 3))])
+
+PAR_OK = 0
+STATUS_NAMES = {0: "PAR_OK", -1: "PAR_ERR_INVALID_ARG", -2: "PAR_ERR_NO_DEVICE",
+                -3: "PAR_ERR_CUDA", -4: "PAR_ERR_OUT_OF_MEMORY", -5: "PAR_ERR_BAD_SCENE",
+                -6: "PAR_ERR_STATE", -7: "PAR_ERR_NCCL"}
+
+# every symbol include/par/par.h declares (checked by tests/test_abi.py)
+EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_set_stream",
+           "par_sync", "par_alloc_host", "par_free_host", "par_set_atlas", "par_set_scene",
+           "par_rebuild_grid", "par_render", "par_render_device", "par_device_frame",
+           "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
+           "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
+           "par_light_default", "par_scene_synthetic", "par_apply_key", "par_draw_overlay"]
+
+
+class Config(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("length", C.c_int32),
+                ("device", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("ambient", C.c_float), ("reserved", C.c_int32 * 5)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("ms_grid_build", C.c_float), ("ms_primary", C.c_float), ("ms_shade", C.c_float),
+                ("ms_total", C.c_float), ("kernel_launches", C.c_int32),
+                ("n_entities", C.c_int32), ("n_survivors", C.c_int32), ("n_inserts", C.c_int32),
+                ("rays", C.c_uint64), ("slab_tests", C.c_uint64), ("reserved", C.c_int32 * 4)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+
+
+class ParError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"{STATUS_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def lib():
+    """Load libpar_b200.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run pixel-art-raytracer_b200/build_native.sh "
+                              "(or __graft_entry__.build()); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i32 = C.c_void_p, C.c_int
+        L.par_create.argtypes = [C.POINTER(vp), C.POINTER(Config)]
+        L.par_destroy.argtypes = [vp]
+        L.par_destroy.restype = None
+        L.par_last_error.restype = C.c_char_p
+        L.par_version.restype = C.c_char_p
+        L.par_set_stream.argtypes = [vp, vp]
+        L.par_sync.argtypes = [vp]
+        L.par_alloc_host.argtypes = [C.c_size_t]
+        L.par_alloc_host.restype = vp
+        L.par_free_host.argtypes = [vp]
+        L.par_free_host.restype = None
+        L.par_set_atlas.argtypes = [vp, vp, i32, vp, i32]
+        L.par_set_scene.argtypes = [vp, vp, vp, i32]
+        L.par_rebuild_grid.argtypes = [vp]
+        L.par_render.argtypes = [vp, vp, i32, vp, vp, C.POINTER(Stats)]
+        L.par_render_device.argtypes = [vp, vp, i32, vp]
+        L.par_device_frame.argtypes = [vp]
+        L.par_device_frame.restype = vp
+        L.par_get_gbuffer.argtypes = [vp, vp, vp]
+        L.par_get_grid.argtypes = [vp, vp, vp]
+        L.par_get_stats.argtypes = [vp, C.POINTER(Stats)]
+        L.par_grid_volume.argtypes = [vp]
+        L.par_sprite_tile_floor.argtypes = [vp]
+        L.par_sprite_tile_floor.restype = None
+        L.par_palette_default.argtypes = [vp]
+        L.par_palette_default.restype = None
+        L.par_scene_default.argtypes = [vp, i32]
+        L.par_light_default.argtypes = [vp]
+        L.par_light_default.restype = None
+        L.par_scene_synthetic.argtypes = [i32, i32, i32, C.c_uint64, i32, vp, i32, vp]
+        L.par_scene_synthetic.restype = None
+        L.par_apply_key.argtypes = [i32, vp, vp]
+        L.par_apply_key.restype = None
+        L.par_draw_overlay.argtypes = [i32, i32, vp, vp, i32, i32, vp]
+        L.par_draw_overlay.restype = None
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _check(rc):
+    if rc != PAR_OK:
+        raise ParError(rc, lib().par_last_error().decode())
+
+
+# ---- host-side pieces of the reference (inputs of the path) ---------------------------------
+
+def tile_floor() -> np.ndarray:
+    """make_tile_floor(), sprites.hpp:73-364."""
+    s = np.zeros(1, SPRITE)
+    lib().par_sprite_tile_floor(_p(s))
+    return s
+
+
+def default_palette() -> np.ndarray:
+    p = np.zeros(4, COLOR)
+    lib().par_palette_default(_p(p))
+    return p
+
+
+def scene_default() -> np.ndarray:
+    """The 162 308-entity default scene, alternative.cpp:519-599."""
+    n = lib().par_scene_default(None, 0)
+    a = np.zeros(n, AABB)
+    lib().par_scene_default(_p(a), n)
+    return a
+
+
+def light_default() -> np.ndarray:
+    l = np.zeros(1, LIGHT)
+    lib().par_light_default(_p(l))
+    return l
+
+
+def scene_synthetic(W, H, L, n=10000, n_lights=16, seed=0xB200):
+    a = np.zeros(n, AABB)
+    l = np.zeros(n_lights, LIGHT)
+    lib().par_scene_synthetic(W, H, L, seed, n, _p(a), n_lights, _p(l))
+    return a, l
+
+
+def apply_key(key: str, boxes: np.ndarray, lights: np.ndarray) -> None:
+    lib().par_apply_key(ord(key), _p(boxes), _p(lights))
+
+
+def draw_overlay(W, H, gbuf, lights, frame, cx=0, cy=0) -> None:
+    lib().par_draw_overlay(W, H, _p(gbuf), _p(lights), cx, cy, _p(frame))
+
+
+def pinned_empty(shape, dtype) -> np.ndarray:
+    """numpy array over page-locked host memory from par_alloc_host (kept alive by the array)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    ptr = lib().par_alloc_host(max(n, 1))
+    if not ptr:
+        raise MemoryError(lib().par_last_error().decode())
+    buf = (C.c_uint8 * n).from_address(ptr)
+    arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+    _PINNED[arr.__array_interface__["data"][0]] = ptr
+    return arr
+
+
+_PINNED: dict[int, int] = {}
+
+
+# ---- the render path ------------------------------------------------------------------------
+
+class Renderer:
+    """One par_ctx: the device-resident state behind the reference's frame loop body.
+
+    Mirrors the call shape of alternative.cpp:689-760:
+        set_scene(aabbs)      <- memset + count_entities_in_bins
+        render(lights)        <- trace_hash_for_pixel + shading loop, returns Color[H][W]
+    """
+
+    def __init__(self, W, H, L, device=0, row_begin=0, row_end=0, ambient=0.0):
+        self.W, self.H, self.L = W, H, L
+        self._h = C.c_void_p()
+        cfg = Config(W, H, L, device, row_begin, row_end, ambient)
+        self.row_begin = row_begin
+        self.row_end = row_end if (row_begin or row_end) else H
+        _check(lib().par_create(C.byref(self._h), C.byref(cfg)))
+
+    def close(self):
+        if self._h:
+            lib().par_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream: int | None):
+        _check(lib().par_set_stream(self._h, cuda_stream))
+
+    def sync(self):
+        _check(lib().par_sync(self._h))
+
+    def set_atlas(self, sprites=None, palette=None):
+        sprites = tile_floor() if sprites is None else np.ascontiguousarray(sprites, SPRITE)
+        palette = default_palette() if palette is None else np.ascontiguousarray(palette, COLOR)
+        _check(lib().par_set_atlas(self._h, _p(sprites), len(sprites), _p(palette), len(palette)))
+
+    def set_scene(self, aabbs, sprite_ids=None):
+        aabbs = np.ascontiguousarray(aabbs, AABB)
+        if sprite_ids is not None:
+            sprite_ids = np.ascontiguousarray(sprite_ids, np.int32)
+        _check(lib().par_set_scene(self._h, _p(aabbs), _p(sprite_ids), len(aabbs)))
+
+    def rebuild_grid(self):
+        _check(lib().par_rebuild_grid(self._h))
+
+    def render(self, lights, out=None, want_gbuf=False):
+        """par_render: returns rgba (H,W) COLOR [, gbuf (H,W) PIXEL], stats dict."""
+        lights = np.ascontiguousarray(lights, LIGHT)
+        rgba = np.zeros((self.H, self.W), COLOR) if out is None else out
+        gbuf = np.zeros((self.H, self.W), PIXEL) if want_gbuf else None
+        st = Stats()
+        _check(lib().par_render(self._h, _p(lights), len(lights), _p(rgba), _p(gbuf), C.byref(st)))
+        return (rgba, gbuf, st.as_dict()) if want_gbuf else (rgba, st.as_dict())
+
+    def render_device(self, lights, d_rgba: int | None = None):
+        """par_render_device: asynchronous, into HBM (own frame buffer when d_rgba is None)."""
+        lights = np.ascontiguousarray(lights, LIGHT)
+        _check(lib().par_render_device(self._h, _p(lights), len(lights), d_rgba))
+
+    def device_frame(self) -> int:
+        return lib().par_device_frame(self._h)
+
+    def gbuffer(self, want_texel=True):
+        gbuf = np.zeros((self.H, self.W), PIXEL)
+        texel = np.full((self.H, self.W), -1, np.int32) if want_texel else None
+        _check(lib().par_get_gbuffer(self._h, _p(gbuf), _p(texel)))
+        return gbuf, texel
+
+    def grid(self):
+        V = lib().par_grid_volume(self._h)
+        count = np.zeros(V, np.int32)
+        ids = np.zeros(V * 8, np.int32)
+        _check(lib().par_get_grid(self._h, _p(count), _p(ids)))
+        return count, ids.reshape(V, 8)
+
+    def stats(self):
+        st = Stats()
+        _check(lib().par_get_stats(self._h, C.byref(st)))
+        return st.as_dict()
