@@ -1,0 +1,62 @@
+"""The C-ABI library loads without a GPU and exports every symbol include/par/par.h
+declares; without a device the entry point fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "par", "par.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(par_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_exports_every_declared_symbol(par):
+    L = par.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 25
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in par.h but not exported"
+    assert sorted(par.EXPORTS) == declared  # the binding covers the whole header
+
+
+def test_pod_layouts(par):
+    assert par.AABB.itemsize == 16 and par.SPRITE.itemsize == 16000
+    assert par.PIXEL.itemsize == 28 and par.LIGHT.itemsize == 8 and par.COLOR.itemsize == 4
+    assert C.sizeof(par.Config) == 48 and C.sizeof(par.Stats) == 64
+
+
+def test_no_cpu_fallback(par):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(par.ParError) as e:
+        par.Renderer(480, 320, 320)
+    assert e.value.code == -2  # PAR_ERR_NO_DEVICE
+
+
+def test_argument_validation(par):
+    h = C.c_void_p()
+    assert par.lib().par_create(C.byref(h), None) == -1
+    bad = par.Config(481, 320, 320, 0, 0, 0, 0.0)
+    assert par.lib().par_create(C.byref(h), C.byref(bad)) == -1
+    assert b"multiples of 40" in par.lib().par_last_error()
+    assert par.lib().par_set_scene(None, None, None, 0) == -1
+    assert par.lib().par_render(None, None, 0, None, None, None) == -1
+
+
+def test_product_never_touches_the_oracle():
+    """The shipped package must not import, link or name anything under oracle/."""
+    pkg = os.path.join(ROOT, "pixel-art-raytracer_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp", ".sh", ".txt")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "liboracle" not in text and "import oracle" not in text and \
+                    "from oracle" not in text, os.path.join(dirpath, f)

@@ -1,0 +1,343 @@
+"""GPU parity: the CUDA path, called through the C ABI, against the oracle (same seeded
+inputs) and against the reference's golden hashes.  Bar: bit-exact — grid contents, hit
+entity ids, texel indices, world y/z, G-buffer bytes and final RGBA8 (SURVEY.md §8d
+"Tolerance": integer outputs and RGBA exact; fp32 intermediates are not exported, their
+0-ULP agreement is implied by exact RGBA on scenes with non-axis-aligned normals)."""
+import numpy as np
+import pytest
+
+from conftest import sha256
+
+pytestmark = pytest.mark.gpu
+
+
+def _u32(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def _render_both(par, O, W, H, L, boxes, lights, atlas=None, palette=None, sprite_ids=None,
+                 check_grid=True):
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas(atlas, palette)
+        r.set_scene(boxes, sprite_ids)
+        rgba, gbuf, stats = r.render(lights, want_gbuf=True)
+        gbuf2, texel = r.gbuffer()
+        grid = r.grid() if check_grid else None
+    ref = O.render(W, H, L, np.ascontiguousarray(boxes, O.AABB), np.ascontiguousarray(lights, O.LIGHT),
+                   atlas=None if atlas is None else np.ascontiguousarray(atlas, O.SPRITE),
+                   palette=None if palette is None else np.ascontiguousarray(palette, O.COLOR),
+                   sprite_ids=sprite_ids)
+    assert gbuf.tobytes() == gbuf2.tobytes()
+    if check_grid:
+        count, bin_box, bin_ent = O.grid_build(W, H, L, np.ascontiguousarray(boxes, O.AABB))
+        assert np.array_equal(grid[0], count), "bin counts (alternative.cpp:262-264)"
+        slot = np.arange(8)[None, :]
+        live = slot < count[:, None]
+        assert np.array_equal(np.where(live, grid[1], -1), np.where(live, bin_ent.reshape(-1, 8), -1)), \
+            "entity-index map in slot order (quirk Q2)"
+    return (rgba, gbuf, texel, stats), ref
+
+
+def _assert_frame_equal(got, ref):
+    rgba, gbuf, texel, _ = got
+    for name in ("entity", "y", "z"):
+        assert np.array_equal(gbuf[name], ref["gbuf"][name]), f"G-buffer {name}"
+    assert np.array_equal(texel, ref["texel"]), "texel index"
+    assert gbuf.tobytes() == ref["gbuf"].tobytes(), "raw Pixel[] bytes"
+    bad = np.argwhere(_u32(rgba) != _u32(ref["rgba"]))
+    assert len(bad) == 0, f"{len(bad)} RGBA pixels differ, first at (row, col) {bad[:5].tolist()}"
+
+
+def _random_atlas(rng, n_sprites, n_palette, axis_aligned=False):
+    from par_b200 import SPRITE, COLOR
+    atlas = np.zeros(n_sprites, SPRITE)
+    atlas["color"] = rng.integers(0, n_palette, (n_sprites, 800))
+    atlas["depth"] = rng.integers(0, 20, (n_sprites, 800))
+    nrm = rng.standard_normal((n_sprites, 800, 3)).astype(np.float32)
+    if axis_aligned:
+        nrm = np.eye(3, dtype=np.float32)[rng.integers(0, 3, (n_sprites, 800))] * \
+            rng.choice([-1.0, 1.0], (n_sprites, 800, 1)).astype(np.float32)
+    atlas["normal"] = nrm
+    pal = np.zeros(n_palette, COLOR)
+    for ch in "rgba":
+        pal[ch] = rng.integers(0, 256, n_palette)
+    return atlas, pal
+
+
+def _random_scene(rng, W, H, L, n, n_lights, cubes=False, n_sprites=1):
+    from par_b200 import AABB, LIGHT
+    a = np.zeros(n, AABB)
+    a["px"] = rng.integers(-30, W + 30, n)
+    a["py"] = rng.integers(-30, 160, n)
+    a["pz"] = rng.integers(-60, L + 60, n)
+    if cubes:
+        a["ex"] = a["ey"] = a["ez"] = 20
+    else:
+        a["ex"] = rng.integers(1, 21, n)
+        a["ey"] = rng.integers(0, 21, n)
+        a["ez"] = rng.integers(0, 21, n)
+    l = np.zeros(n_lights, LIGHT)
+    l["x"] = rng.integers(-100, W + 200, n_lights)
+    l["y"] = rng.integers(-50, 400, n_lights)
+    l["z"] = rng.integers(-100, L + 100, n_lights)
+    l["radius"] = 10
+    ids = rng.integers(0, n_sprites, n).astype(np.int32) if n_sprites > 1 else None
+    return a, l, ids
+
+
+# ------------------------------------------------------------------ reference scenes
+
+def test_c1_default_scene(par, oracle, golden):
+    """Config 1: the reference's default scene at its built-in 480x320."""
+    got, ref = _render_both(par, oracle, 480, 320, 320, par.scene_default(), par.light_default())
+    _assert_frame_equal(got, ref)
+    g = golden["tier1_480x320x320_frame0"]
+    assert sha256(got[0]) == g["frame0_pre_overlay_sha256"]
+    assert sha256(got[1]) == g["gbuf0_sha256"]
+    # with the host-side overlay the frame equals the UNMODIFIED reference's
+    frame = got[0].copy()
+    par.draw_overlay(480, 320, got[1], par.light_default(), frame)
+    assert sha256(frame) == golden["tier0_480x320x320_frame0"]["frame0_sha256"]
+    assert got[3]["n_survivors"] == 968 and got[3]["n_inserts"] == 1095
+
+
+@pytest.mark.parametrize("size,key", [((1920, 1080, 1080), "tier1_1920x1080x1080_frame0"),
+                                      ((3840, 2160, 2160), "tier1_3840x2160x2160_frame0")])
+def test_default_scene_large_views_vs_reference_hashes(par, golden, size, key):
+    """Configs 2 and 4 (frame 0): full-size frames against hashes of the real reference's
+    output — no oracle involved."""
+    W, H, L = size
+    g = golden[key]
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(par.scene_default())
+        rgba, gbuf, _ = r.render(par.light_default(), want_gbuf=True)
+    assert sha256(gbuf) == g["gbuf0_sha256"]
+    assert sha256(rgba) == g["frame0_pre_overlay_sha256"]
+    frame = rgba.copy()
+    par.draw_overlay(W, H, gbuf, par.light_default(), frame)
+    assert sha256(frame) == g["frame0_sha256"]
+
+
+def test_script_d_frames_vs_reference_hashes(par, oracle, golden):
+    """Config 4: per-frame scene upload + render under key script D (player and light move),
+    FNV-1a-64 of every sampled frame (overlay applied) against the real reference's."""
+    want = golden["tier1_1920x1080x1080_scriptD_240"]["fnv1a64"]
+    boxes, lights = par.scene_default(), par.light_default()
+    W, H, L = 1920, 1080, 1080
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        for f in range(240):
+            for k in oracle.script_keys("D", f):
+                par.apply_key(k, boxes, lights)
+            if f % 8 == 0 or f == 239:
+                r.set_scene(boxes)
+                rgba, gbuf, _ = r.render(lights, want_gbuf=True)
+                par.draw_overlay(W, H, gbuf, lights, rgba)
+                assert "%016x" % oracle.fnv1a64(rgba) == want[f], f"frame {f}"
+
+
+def test_script_c_frames_480(par, oracle, golden):
+    want = golden["tier0_480x320x320_scriptC_240"]["fnv1a64"]
+    boxes, lights = par.scene_default(), par.light_default()
+    with par.Renderer(480, 320, 320) as r:
+        r.set_atlas()
+        for f in range(240):
+            for k in oracle.script_keys("C", f):
+                par.apply_key(k, boxes, lights)
+            r.set_scene(boxes)
+            rgba, gbuf, _ = r.render(lights, want_gbuf=True)
+            par.draw_overlay(480, 320, gbuf, lights, rgba)
+            assert "%016x" % oracle.fnv1a64(rgba) == want[f], f"frame {f}"
+
+
+# ------------------------------------------------------------------ synthetic scenes vs oracle
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_scenes_multi_sprite_multi_light(par, oracle, seed):
+    """Random boxes (ragged extents, partly outside the view), random multi-sprite atlas with
+    NON-axis-aligned float normals (exposes any FMA contraction or reordering), lights inside
+    and outside the grid."""
+    rng = np.random.default_rng(1000 + seed)
+    W, H, L = [(480, 320, 320), (640, 480, 480), (320, 640, 640)][seed % 3]
+    n_sprites, n_pal = 1 + seed % 5 * 3, 2 + seed
+    atlas, pal = _random_atlas(rng, n_sprites, n_pal)
+    boxes, lights, ids = _random_scene(rng, W, H, L, 1500 + 700 * seed, 1 + 3 * seed,
+                                       n_sprites=n_sprites)
+    got, ref = _render_both(par, oracle, W, H, L, boxes, lights, atlas, pal, ids)
+    _assert_frame_equal(got, ref)
+
+
+def test_dense_overflowing_bins(par, oracle):
+    """Quirk Q2: many entities per bin so that rings wrap (n = 8, 9, 16, 17 ... inserts)."""
+    rng = np.random.default_rng(7)
+    W, H, L = 480, 320, 320
+    boxes, lights, _ = _random_scene(rng, W, H, L, 9000, 4, cubes=True)
+    count = oracle.grid_build(W, H, L, np.ascontiguousarray(boxes, oracle.AABB))[0]
+    got, ref = _render_both(par, oracle, W, H, L, boxes, lights)
+    _assert_frame_equal(got, ref)
+    assert got[3]["n_inserts"] > 8 * np.count_nonzero(count)  # bins did wrap
+
+
+def test_c3_recipe_reduced(par, oracle):
+    """The C3 recipe at a view the oracle renders in seconds."""
+    W, H, L = 1280, 720, 720
+    boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=16)
+    got, ref = _render_both(par, oracle, W, H, L, boxes, lights)
+    _assert_frame_equal(got, ref)
+
+
+def test_c3_full_size_row_sample(par, oracle):
+    """Config 3 at full size (3840x2160, 10k sprites, 16 lights): the whole frame on the GPU,
+    the oracle on three row bands (the grid is always built whole)."""
+    W, H, L = 3840, 2160, 2160
+    boxes, lights = par.scene_synthetic(W, H, L)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        rgba, gbuf, stats = r.render(lights, want_gbuf=True)
+    assert stats["n_survivors"] == 9750 and stats["n_inserts"] == 40832
+    for row0 in (0, 1013, 2120):
+        ref = oracle.render(W, H, L, boxes.view(oracle.AABB), lights.view(oracle.LIGHT),
+                            row0=row0, row1=row0 + 40)
+        assert gbuf[row0:row0 + 40].tobytes() == ref["gbuf"][row0:row0 + 40].tobytes()
+        assert np.array_equal(_u32(rgba[row0:row0 + 40]), _u32(ref["rgba"][row0:row0 + 40]))
+
+
+# ------------------------------------------------------------------ quirk micro-scenes
+
+def _cube(x, y, z, e=20):
+    return (x, y, z, e, e, e, (0, 0))
+
+
+def test_quirk_nan_slab_and_zero_direction(par, oracle):
+    """Q13: lights whose x/y/z equals pixel coordinates and box faces (0 * inf = NaN through
+    std::min/std::max), and a light exactly ON a visible surface point (0/0 direction)."""
+    from par_b200 import AABB, LIGHT
+    boxes = np.array([_cube(100, 0, 100), _cube(120, 0, 100), _cube(100, 20, 120),
+                      _cube(200, 0, 60), _cube(200, 40, 60), _cube(240, 0, 140),
+                      _cube(60, 0, 200), _cube(60, 20, 200), _cube(300, 0, 100)], AABB)
+    lights = np.zeros(6, LIGHT)
+    lights["x"] = [100, 120, 210, 260, 60, 300]
+    lights["y"] = [20, 40, 20, 20, 60, 20]     # top faces are at y = 20 / 40 / 60
+    lights["z"] = [100, 120, 70, 140, 200, 110]
+    got, ref = _render_both(par, oracle, 480, 320, 320, boxes, lights)
+    _assert_frame_equal(got, ref)
+
+
+def test_quirk_depth_ties_and_early_out(par, oracle):
+    """Q8 (ties keep the first in bin_z/slot order) and Q9 (two adjacent hit bins end the
+    march; an empty bin resets the run)."""
+    from par_b200 import AABB
+    rows = []
+    for k in range(6):           # identical depth keys: same y - z
+        rows.append(_cube(40, 10 + 5 * k, 10 + 5 * k))
+    for k in range(5):           # stacks along z in adjacent bins, all covering the same pixels
+        rows.append(_cube(200, 0, 40 * k + 10))
+        rows.append(_cube(200, 30, 40 * k + 10))
+    rows += [_cube(320, 0, 20), _cube(320, 0, 100), _cube(320, 50, 180), _cube(320, 90, 260)]
+    boxes = np.array(rows, AABB)
+    got, ref = _render_both(par, oracle, 480, 320, 320, boxes, par.light_default())
+    _assert_frame_equal(got, ref)
+
+
+def test_quirk_light_outside_grid_and_far_away(par, oracle):
+    """Q18: light bins outside the grid on every side, including walks longer than one CTA's
+    worth of steps (more than 320 bins away)."""
+    from par_b200 import LIGHT
+    rng = np.random.default_rng(3)
+    boxes, _, _ = _random_scene(rng, 480, 320, 320, 1200, 1, cubes=True)
+    lights = np.zeros(8, LIGHT)
+    lights["x"] = [480, -500, 20000, 240, 240, -32000, 30000, 100]
+    lights["y"] = [160, 100, 300, 5000, -4000, 32000, -32000, 50]
+    lights["z"] = [80, -300, 150, 100, 20000, 100, 32000, -16000]
+    got, ref = _render_both(par, oracle, 480, 320, 320, boxes, lights)
+    _assert_frame_equal(got, ref)
+
+
+def test_empty_and_degenerate_scenes(par, oracle):
+    from par_b200 import AABB, LIGHT
+    got, ref = _render_both(par, oracle, 480, 320, 320, np.zeros(0, AABB), par.light_default())
+    _assert_frame_equal(got, ref)
+    assert sha256(got[0]) == sha256(np.full((320, 480), 31 | 31 << 8 | 31 << 16, np.uint32))  # Q10
+    # zero lights: ambient only
+    got, ref = _render_both(par, oracle, 480, 320, 320, par.scene_default()[:2000],
+                            np.zeros(0, LIGHT))
+    _assert_frame_equal(got, ref)
+    # zero-extent boxes are legal and invisible
+    flat = np.array([(100, 0, 100, 20, 0, 0, (0, 0)), (150, 0, 100, 0, 20, 20, (0, 0))], AABB)
+    got, ref = _render_both(par, oracle, 480, 320, 320, flat, par.light_default())
+    _assert_frame_equal(got, ref)
+
+
+def test_maximum_lights(par, oracle):
+    rng = np.random.default_rng(11)
+    boxes, lights, _ = _random_scene(rng, 480, 320, 320, 2500, 64, cubes=True)
+    got, ref = _render_both(par, oracle, 480, 320, 320, boxes, lights)
+    _assert_frame_equal(got, ref)
+
+
+# ------------------------------------------------------------------ bands, errors, properties
+
+def test_row_bands_reassemble(par):
+    """Multi-GPU building block: bands (not multiples of 40) written in place give the
+    single-context frame, byte for byte."""
+    W, H, L = 640, 480, 480
+    boxes, lights = par.scene_synthetic(W, H, L, n=1500, n_lights=5)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        full, gfull, _ = r.render(lights, want_gbuf=True)
+    out = np.zeros((H, W), par.COLOR)
+    gout = np.zeros((H, W), par.PIXEL)
+    for a, b in [(0, 97), (97, 100), (100, 333), (333, 480)]:
+        with par.Renderer(W, H, L, row_begin=a, row_end=b) as r:
+            r.set_atlas()
+            r.set_scene(boxes)
+            band = np.zeros((H, W), par.COLOR)
+            gband = np.zeros((H, W), par.PIXEL)
+            r.render(lights, out=band)
+            g2, _ = r.gbuffer()
+            assert not _u32(band[:a]).any() and not _u32(band[b:]).any()
+            out[a:b] = band[a:b]
+            gout[a:b] = g2[a:b]
+    assert np.array_equal(_u32(out), _u32(full))
+    assert gout.tobytes() == gfull.tobytes()
+
+
+def test_determinism_and_rebuild_idempotence(par):
+    W, H, L = 1920, 1080, 1080
+    boxes, lights = par.scene_synthetic(W, H, L, n=10000, n_lights=8)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        a, _ = r.render(lights)
+        grid_a = r.grid()
+        r.rebuild_grid()
+        r.rebuild_grid()
+        b, _ = r.render(lights)
+        grid_b = r.grid()
+    assert np.array_equal(_u32(a), _u32(b))
+    assert np.array_equal(grid_a[0], grid_b[0]) and np.array_equal(grid_a[1], grid_b[1])
+
+
+def test_error_paths(par):
+    from par_b200 import AABB
+    with par.Renderer(480, 320, 320) as r:
+        with pytest.raises(par.ParError) as e:
+            r.set_scene(par.scene_default())
+        assert e.value.code == -6  # atlas first
+        r.set_atlas()
+        with pytest.raises(par.ParError) as e:
+            r.render(par.light_default())
+        assert e.value.code == -6  # scene first
+        bad = np.array([(10, 0, 10, 30, 20, 20, (0, 0))], AABB)  # extent.x 30 > sprite width
+        r.set_scene(bad)
+        with pytest.raises(par.ParError) as e:
+            r.render(par.light_default())
+        assert e.value.code == -5
+        r.set_scene(par.scene_default()[:100])
+        r.render(par.light_default())  # context stays usable
+        with pytest.raises(par.ParError):
+            r.set_scene(par.scene_default()[:10], sprite_ids=np.full(10, 3, np.int32))
+            r.render(par.light_default())

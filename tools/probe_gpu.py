@@ -1,0 +1,45 @@
+#!/usr/bin/env python
+"""Developer probe: per-kernel CUDA-event times of the render path on the configs of
+BASELINE.json (run under gpurun).  Not a benchmark line; bench.py is."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "pixel-art-raytracer_b200"))
+import par_b200 as par  # noqa: E402
+
+
+def run(name, W, H, L, boxes, lights, reps=5):
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        best = None
+        for _ in range(reps):
+            r.rebuild_grid()
+            t0 = time.perf_counter()
+            rgba, st = r.render(lights)
+            st["wall_ms"] = (time.perf_counter() - t0) * 1e3
+            if best is None or st["ms_total"] < best["ms_total"]:
+                best = st
+        best["config"] = name
+        best["mrays_s_kernels"] = best["rays"] / best["ms_total"] / 1e3
+        print(json.dumps(best), flush=True)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["c1", "c4", "c2", "c3", "c5"]
+    d, l = par.scene_default(), par.light_default()
+    if "c1" in which:
+        run("C1 default 480x320", 480, 320, 320, d, l)
+    if "c4" in which:
+        run("C4 default 1920x1080 frame0", 1920, 1080, 1080, d, l)
+    if "c2" in which:
+        run("C2 default 3840x2160", 3840, 2160, 2160, d, l)
+    if "c3" in which:
+        run("C3 synthetic 10k/16 lights 3840x2160", 3840, 2160, 2160, *par.scene_synthetic(3840, 2160, 2160))
+    if "c5" in which:
+        run("C5 synthetic 10k/16 lights 7680x4320", 7680, 4320, 4320, *par.scene_synthetic(7680, 4320, 4320))
+        run("C5b synthetic 40k/16 lights 7680x4320", 7680, 4320, 4320,
+            *par.scene_synthetic(7680, 4320, 4320, n=40000))
