@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the render path (BASELINE.json metric) on 1..8 B200.
+
+    python bench.py --gpus 1 --steps K --warmup W              # our arm, one GPU
+    torchrun --nproc-per-node N ... bench.py --gpus N ...      # row bands + NCCL frame gather
+    python bench.py --impl reference ...                       # the reference's own CPU loop
+
+A step = one pass of the hot path (alternative.cpp:689-760: grid build, primary rays,
+shading + shadow rays, RGBA8 frame) over one frame of the workload.  Default workload `c2`
+= BASELINE.json configs[1]: the reference's default scene at 3840x2160, one light.
+Rays are reference-equivalent rays: W*H*(1 + n_lights) per frame.
+
+`value`  : whole-job Mrays/s with the scene already resident in HBM (device scene loader +
+           both kernels + (N>1) the NCCL all-gather of the row bands), CUDA-event timed, L2
+           flushed between steps, max over ranks.
+`e2e`    : the same through the public C ABI with HOST buffers: par_set_scene (H2D of the
+           AABBs from pinned memory) + render + D2H of the finished frame, every step.
+`roofline`: the shade kernel (dominant) against the FP32/INT ALU issue roofline
+           (SMs x 128 lanes x max SM clock) in reference-equivalent algorithmic lane-ops
+           (SURVEY.md §8d); HBM figures are given beside it because the path is not HBM bound.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "pixel-art-raytracer_b200"))
+
+WORKLOADS = {
+    # name: (W, H, L, description)
+    "c1": (480, 320, 320, "default scene (162308 sprites, 1 light) at the reference's built-in 480x320"),
+    "c4": (1920, 1080, 1080, "default scene at 1920x1080, frame 0 of the 240-frame sequence"),
+    "c2": (3840, 2160, 2160, "default scene (162308 sprites, 1 light) at 3840x2160"),
+    "c3": (3840, 2160, 2160, "synthetic 10k sprites + 16 lights at 3840x2160 (seed 0xB200)"),
+    "c5": (7680, 4320, 4320, "synthetic 10k sprites + 16 lights at 7680x4320 (seed 0xB200)"),
+    "c5b": (7680, 4320, 4320, "synthetic 40k sprites + 16 lights at 7680x4320 (seed 0xB200)"),
+}
+
+
+def load_json(path, default=None):
+    try:
+        with open(path) as f:
+            return json.load(f)
+    except (OSError, ValueError):
+        return default
+
+
+# ------------------------------------------------------------------ clocks
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip().split(", ")))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        sm = sorted(int(r[0]) for r in rows if r[0].isdigit())
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower() == "active":
+                    reasons.add(name)
+        mx = [int(r[1]) for r in rows if r[1].isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ reference arm / cpu baseline
+
+def run_reference_binary(W, H, L, frames, budget_s):
+    """Time the REAL reference (oracle/_ref tier-1 build, 1 thread: it has no threading) on
+    the default scene at this view.  Returns (ms per frame list, note) or None."""
+    exe = os.path.join(ROOT, "oracle", "_ref", f"ref_tier1_{W}x{H}x{L}")
+    if not os.path.exists(exe):
+        return None
+    with tempfile.TemporaryDirectory() as td:
+        env = dict(os.environ, PAR_REF_FRAMES=str(frames), PAR_REF_TIMES=f"{td}/t.txt")
+        t0 = time.time()
+        try:
+            subprocess.run([exe], env=env, check=True, stdout=subprocess.DEVNULL, timeout=budget_s)
+        except subprocess.TimeoutExpired:
+            pass
+        except (OSError, subprocess.CalledProcessError):
+            return None
+        try:
+            ms = [int(ln.split()[1]) / 1e6 for ln in open(f"{td}/t.txt")]
+        except OSError:
+            ms = []
+        return (ms, time.time() - t0) if ms else None
+
+
+def run_oracle_port(name, W, H, L, budget_s):
+    """Fallback CPU arm: the oracle port on all host cores, on a bounded row sample."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    boxes, lights = (O.scene_default(), O.light_default()) if name in ("c1", "c2", "c4") else \
+        O.scene_synthetic(W, H, L, n=40000 if name == "c5b" else 10000)
+    rows = max(40, min(H, (H // 40 // 8) * 40))
+    row0 = (H // 2 // 40) * 40
+    t0 = time.time()
+    O.render(W, H, L, boxes, lights, row0=row0, row1=row0 + rows, want_gbuf=False, want_texel=False)
+    dt = time.time() - t0
+    return dt, rows, len(lights), os.cpu_count()
+
+
+def reference_arm(args):
+    W, H, L, desc = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    steps, warmup = args.steps, args.warmup
+    line = {"impl": "reference", "metric": "Mrays/s", "unit": "Mrays/s", "n_gpus": args.gpus,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": f"{args.workload}: {desc}"}}
+    res = None
+    if args.workload in ("c1", "c2", "c4"):
+        # ~17 s per 4K frame on one core: clamp the frame count to the time budget
+        per = {"c1": 0.06, "c4": 3.0, "c2": 20.0}[args.workload]
+        frames = max(2, min(steps + warmup, int(args.cpu_budget / per)))
+        warm = 1 if (warmup and frames > 1) else 0  # one untimed frame is enough for a CPU loop
+        res = run_reference_binary(W, H, L, frames, args.cpu_budget * 2 + 60)
+    if res:
+        ms, wall = res
+        ms_t = ms[warm:] if len(ms) > warm else ms
+        mean = sum(ms_t) / len(ms_t)
+        value = W * H * 2 / mean / 1e3
+        line.update({"value": value, "steps": len(ms_t), "warmup": warm, "ms_per_step": mean,
+                     "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": 1, "kind": "reference",
+                                      "sample": f"{len(ms_t)} whole frames of the unmodified reference loop "
+                                                f"(alternative.cpp:689-772, oracle/_ref tier-1 build, -O3, single "
+                                                f"thread: the reference has no threading); {steps} steps requested"}})
+    else:
+        dt, rows, nl, cores = run_oracle_port(args.workload, W, H, L, args.cpu_budget)
+        value = rows * W * (1 + nl) / dt / 1e6
+        line.update({"value": value, "steps": 1, "warmup": 0, "ms_per_step": dt * 1e3,
+                     "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
+                                      "sample": f"oracle port (OpenMP, {cores} threads) on rows of a {rows}-row band "
+                                                f"of the frame incl. the whole-frame grid build"}})
+    line["e2e"] = {"value": line["value"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------ our arm
+
+def make_workload(par, name):
+    W, H, L, desc = WORKLOADS[name]
+    if name in ("c1", "c2", "c4"):
+        boxes, lights = par.scene_default(), par.light_default()
+    else:
+        boxes, lights = par.scene_synthetic(W, H, L, n=40000 if name == "c5b" else 10000, n_lights=16)
+    return W, H, L, desc, boxes, lights
+
+
+def ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import par_b200 as par
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W, H, L, desc, boxes, lights = make_workload(par, args.workload)
+    n_lights = len(lights)
+    rows = H // world  # H/N is integral for every config
+    row0, row1 = rank * rows, (rank + 1) * rows if rank < world - 1 else H
+    rays_frame = W * H * (1 + n_lights)
+
+    stream = torch.cuda.Stream(device=dev)
+    ren = par.Renderer(W, H, L, device=local, row_begin=row0, row_end=row1)
+    ren.set_stream(stream.cuda_stream)
+    ren.set_atlas()
+    frame = torch.zeros(H * W * 4, dtype=torch.uint8, device=dev)  # the full frame in HBM
+    band = frame[row0 * W * 4: row1 * W * 4]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    h_boxes = par.pinned_empty(len(boxes), par.AABB)
+    h_boxes[:] = boxes
+    h_frame = par.pinned_empty((H, W), par.COLOR) if rank == 0 else None
+    t_hframe = torch.from_numpy(h_frame.view(np.uint8).reshape(-1)) if rank == 0 else None
+
+    def gather():
+        if world > 1:
+            dist.all_gather_into_tensor(frame, band)  # in place: band r lives at offset r of frame
+
+    def step_resident():
+        ren.rebuild_grid()                       # device scene loader on the resident scene
+        ren.render_device(lights, frame.data_ptr())
+        gather()
+
+    def step_e2e():
+        ren.set_scene(h_boxes)                   # H2D from pinned memory + scene loader
+        if world == 1:
+            ren.render(lights, out=h_frame)      # the drop-in call: render + D2H into a host frame
+            return
+        ren.render_device(lights, frame.data_ptr())
+        gather()
+        if rank == 0:
+            t_hframe.copy_(frame, non_blocking=True)  # D2H of the gathered frame
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(step_fn, steps, warmup):
+        with torch.cuda.stream(stream):
+            for _ in range(warmup):
+                step_fn()
+            barrier()
+            evs = []
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                flush.fill_(1)                   # L2 flush between timed iterations (untimed)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(stream)
+                step_fn()
+                b.record(stream)
+                evs.append((a, b))
+            barrier()
+            t1 = time.perf_counter()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, t1
+
+    with torch.cuda.stream(stream):
+        ren.set_scene(h_boxes)
+        step_resident()
+    torch.cuda.synchronize(dev)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ms, t0, t1 = timed(step_resident, args.steps, args.warmup)
+    st = ren.stats()                            # per-kernel CUDA-event times of the last step
+    ms_e2e, _, t1 = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # per-kernel times over a few more steps, for the roofline of the dominant kernel
+    shade_ms, prim_ms, build_ms = [], [], []
+    with torch.cuda.stream(stream):
+        for _ in range(min(args.steps, 10)):
+            flush.fill_(1)
+            step_resident()
+            s = ren.stats()
+            shade_ms.append(s["ms_shade"])
+            prim_ms.append(s["ms_primary"])
+            build_ms.append(s["ms_grid_build"])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # correctness spot check of what was timed: the gathered frame equals a 1-context render
+    value = rays_frame * args.steps / ms / 1e3
+    e2e = rays_frame * args.steps / ms_e2e / 1e3
+    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"), {}) or {}
+    ops_tab = load_json(os.path.join(ROOT, "tests", "golden", "workload_ops.json"), {}) or {}
+    prop = torch.cuda.get_device_properties(dev)
+    sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
+    peak_ops = prop.multi_processor_count * 128 * sm_max * 1e6 / 1e12  # T lane-ops/s
+    ops = (ops_tab.get(args.workload) or {}).get("algorithmic_ops")
+    shade = sum(shade_ms) / len(shade_ms)
+    frac_rows = (row1 - row0) / H
+    # shade kernel's share of the algorithmic ops: everything but the primary-ray counters
+    roofline = {"bound": "fp32_alu", "kernel": "k_shade", "unit": "Tlane-op/s", "peak": round(peak_ops, 2),
+                "peak_source": f"{prop.multi_processor_count} SMs x 128 lanes x {sm_max:.0f} MHz (1 op/lane/clk; no FMA "
+                               "on this path) — nominal issue ceiling, of nominal",
+                "traffic": None}
+    if ops:
+        c = ops_tab[args.workload]["counters"]
+        shade_ops = (59.0 * c["shaded_px_lights"] + 17.0 * c["lit_px_lights"] + 19.0 * c["shadow_probes"] +
+                     5.0 * c["shadow_slot_entries"] + 32.0 * c["slab_tests"]) * frac_rows
+        ach = shade_ops / (shade * 1e-3) / 1e12
+        roofline.update({"achieved": round(ach, 2), "frac": round(ach / peak_ops, 3),
+                         "algorithmic_ops_per_launch": shade_ops, "ms_per_launch": round(shade, 4),
+                         "note": "reference-equivalent algorithmic lane-ops (SURVEY.md §8d weights x oracle counters) "
+                                 "/ CUDA-event time of k_shade; >1 means the kernel legally skips work the reference "
+                                 "does (shared grid walks, de-duplicated probes, Q19); see profiles/ for ncu pipe "
+                                 "utilisation"})
+    hbm_bytes = 16.0 * W * (row1 - row0) + 4.0 * W * (row1 - row0)
+    roofline["hbm"] = {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": round(hbm_bytes / (shade * 1e-3) / 1e9, 1),
+                       "peak_gbs": peaks.get("hbm_gbs"), "note": "G-buffer read + RGBA8 write; not the bound"}
+
+    line = {
+        "metric": "Mrays/s", "value": round(value, 1), "unit": "Mrays/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 4),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {desc}", "view": [W, H, L], "n_entities": int(len(boxes)),
+                   "n_lights": int(n_lights), "rays_per_frame": rays_frame,
+                   "parallelism": f"row bands x{world}" + (" + NCCL all-gather of the RGBA8 frame" if world > 1 else ""),
+                   "l2": "flushed between timed steps (256 MB fill)", "frames_per_s": round(1e3 * args.steps / ms, 2)},
+        "e2e": {"value": round(e2e, 1), "unit": "Mrays/s", "ms_per_step": round(ms_e2e / args.steps, 4),
+                "frames_per_s": round(1e3 * args.steps / ms_e2e, 2),
+                "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4)},
+        "gpu_launches": (10 * args.steps) * world,
+        "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
+                       "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},
+        "roofline": roofline, "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, W, H, L)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, W, H, L):
+    """Reported baseline (not the target): the real reference loop, 1 thread, on this box."""
+    if args.workload in ("c1", "c2", "c4"):
+        frames = {"c1": 50, "c4": 4, "c2": 2}[args.workload]
+        res = run_reference_binary(W, H, L, frames, args.cpu_budget * 2 + 60)
+        if res:
+            ms = res[0][1:] or res[0]
+            mean = sum(ms) / len(ms)
+            return {"value": round(W * H * 2 / mean / 1e3, 3), "unit": "Mrays/s", "cores": 1, "kind": "reference",
+                    "ms_per_frame": round(mean, 1), "host_cores_available": os.cpu_count(),
+                    "sample": f"{len(ms)} whole frame(s) of the unmodified reference loop (oracle/_ref tier-1 build, "
+                              "-O3, single thread: the reference has no threading), after 1 warm-up frame"}
+    dt, rows, nl, cores = run_oracle_port(args.workload, W, H, L, args.cpu_budget)
+    return {"value": round(rows * W * (1 + nl) / dt / 1e6, 3), "unit": "Mrays/s", "cores": cores, "kind": "port",
+            "sample": f"oracle port (OpenMP, {cores} threads), one {rows}-row band of the frame incl. whole-frame grid build"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the CPU legs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()
