@@ -82,6 +82,7 @@ struct par_ctx {
     // grid
     int* d_cnt = nullptr;
     int* d_ids = nullptr;
+    unsigned* d_occ_mask = nullptr;
     LoaderCounters* d_ctr = nullptr;
     LoaderCounters* h_ctr = nullptr;  // pinned
     // atlas
@@ -120,7 +121,7 @@ int run_loader(par_ctx* c) {
     PAR_CUDA(cudaEventRecord(c->ev_build0, c->stream));
     PAR_CUDA(launch_scene_loader(c->d_raw, c->has_sprite_ids ? c->d_sprite_ids : nullptr,
                                  c->n_entities, c->n_sprites, c->d, c->d_boxes, c->d_cnt, c->d_ids,
-                                 c->d_survivors, c->d_ctr, c->stream, &c->launches_build));
+                                 c->d_occ_mask, c->d_survivors, c->d_ctr, c->stream, &c->launches_build));
     PAR_CUDA(cudaEventRecord(c->ev_build1, c->stream));
     PAR_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(LoaderCounters), cudaMemcpyDeviceToHost,
                              c->stream));
@@ -199,6 +200,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
         size_t px = (size_t)d.W * d.H;
         PAR_CUDA(cudaMalloc(&c->d_cnt, sizeof(int) * (size_t)d.V));
         PAR_CUDA(cudaMalloc(&c->d_ids, sizeof(int) * (size_t)d.V * kSlots));
+        PAR_CUDA(cudaMalloc(&c->d_occ_mask, sizeof(unsigned) * (((size_t)d.V + 31) / 32)));
         PAR_CUDA(cudaMalloc(&c->d_ctr, sizeof(LoaderCounters)));
         PAR_CUDA(cudaMallocHost(&c->h_ctr, sizeof(LoaderCounters)));
         memset(c->h_ctr, 0, sizeof(LoaderCounters));
@@ -207,6 +209,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
         PAR_CUDA(cudaMemsetAsync(c->d_frame, 0, sizeof(uchar4) * px, c->stream));
         PAR_CUDA(cudaMemsetAsync(c->d_gbuf, 0, sizeof(int4) * px, c->stream));
         PAR_CUDA(configure_primary(primary_smem_bytes(d, 1)));
+        PAR_CUDA(configure_shade());
         return PAR_OK;
     }();
     if (rc != PAR_OK) {
@@ -227,6 +230,7 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_survivors);
     cudaFree(c->d_cnt);
     cudaFree(c->d_ids);
+    cudaFree(c->d_occ_mask);
     cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     cudaFree(c->d_atlas_depth);
@@ -340,8 +344,8 @@ int par_set_atlas(par_ctx* c, const par_sprite* sprites, int n_sprites, const pa
 }
 
 int par_set_scene(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n) {
-    if (!c || n < 0 || (n > 0 && !aabbs))
-        return fail(PAR_ERR_INVALID_ARG, "par_set_scene: bad argument%s%s");
+    if (!c || n < 0 || n > (1 << 26) || (n > 0 && !aabbs))
+        return fail(PAR_ERR_INVALID_ARG, "par_set_scene: bad argument (at most 2^26 entities)%s%s");
     if (c->n_sprites == 0) return fail(PAR_ERR_STATE, "par_set_scene: call par_set_atlas first%s%s");
     DeviceGuard guard(c->cfg.device);
     if (n > c->cap_entities) {
@@ -399,6 +403,7 @@ int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d
     sp.d = d;
     sp.cnt = c->d_cnt;
     sp.ids = c->d_ids;
+    sp.occ_mask = c->d_occ_mask;
     sp.boxes = c->d_boxes;
     sp.gbuf = c->d_gbuf;
     sp.atlas_normal = c->d_atlas_normal;

@@ -14,8 +14,8 @@ struct LoaderCounters {
 };
 cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,
                                 const ViewDims& d, int4* boxes, int* cnt, int* ids,
-                                int* survivors, LoaderCounters* ctr, cudaStream_t s,
-                                int* launches);
+                                unsigned* occ_mask, int* survivors, LoaderCounters* ctr,
+                                cudaStream_t s, int* launches);
 
 // ---- primary rays (alternative.cpp:271-383) ----
 struct PrimaryParams {
@@ -38,6 +38,7 @@ struct ShadeParams {
     ViewDims d;
     const int* cnt;
     const int* ids;
+    const unsigned* occ_mask;  // 1 bit per bin: (cnt & 7) != 0
     const int4* boxes;
     const int4* gbuf;
     const float* atlas_normal;         // [n_sprites][800][3]
@@ -50,6 +51,8 @@ struct ShadeParams {
     unsigned long long* slab_counter;  // optional instrumentation (NULL in production)
     short4 lights[kMaxLights];         // x, y, z, radius (alternative.cpp:619-622)
 };
+size_t shade_smem_bytes();
+cudaError_t configure_shade();  // per device, before the first launch
 cudaError_t launch_shade(const ShadeParams& p, cudaStream_t s);
 
 }  // namespace par

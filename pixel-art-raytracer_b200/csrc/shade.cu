@@ -5,32 +5,78 @@
 //     acc = sum over visible lights of max(0, n . t_l);   out = color * min(1, acc + ambient)
 //
 // What makes it fast without changing a bit of the output:
-//  * The reference walks the grid once per PIXEL; but the sequence of probed bins depends only
-//    on (start bin, light bin), and every hit pixel of a 40x40 screen tile starts in bin
-//    (tile x, tile y, z/40) (quirk Q11).  One CTA owns a tile, groups its pixels by z/40 and
-//    walks once per (group, light): the fp32 position chain is accumulated sequentially
-//    exactly as the reference does (quirk Q15), the 7 probes of a step collapse to the
-//    distinct bins among them (probing a bin twice cannot change an OR), and the occupied
-//    bins' boxes are gathered into shared memory.
-//  * The per-pixel work is then a loop of slab tests over that shared list, with the
-//    reference's unbounded-line semantics (Q14), argument-order-exact min/max (Q13), the
-//    start-bin skip (Q16) applied at gather time and the self-entity skip (Q17) per lane.
-//  * A pixel whose Lambert term is 0 for a light never issues the shadow query: visible or
-//    not, it adds +0 (quirk Q19).
-//  * Four neighbouring lanes merge their RGBA8 pixels with shuffles into one 16-byte store.
+//  * The reference walks the grid once per PIXEL and per light; but the sequence of probed
+//    bins depends only on (start bin, light bin), and every hit pixel of a 40x40 screen tile
+//    starts in bin (tile x, tile y, z/40) (quirk Q11).  One CTA owns a tile, groups its pixels
+//    by z/40 ("group"), compacts each group into a dense pixel list, and walks ONCE per
+//    (group, light) — for a whole batch of lights at a time:
+//      phase 1   one thread per run of 8 walk steps: the fp32 position chain is accumulated
+//                sequentially exactly as the reference does (quirk Q15); the 7 probes of a step
+//                collapse to the distinct bins among them; occupied bins (1-bit occupancy mask,
+//                L1 resident) are appended to a shared list;
+//      phase 1b  one lane per occupied bin: fetch its count;
+//      phase 2   one lane per (occupied bin, slot): entity -> box, de-duplicated per light with
+//                a shared-memory hash set (testing a box twice cannot change an OR), written as
+//                float lo/hi corners into the light's segment of a shared box list;
+//      phase 3   one lane per pixel of the group: for every light of the batch, the Lambert
+//                term and — only when it is > 0 (quirk Q19) — a loop of slab tests over that
+//                light's boxes: unbounded-line semantics (Q14), the self-entity skip (Q17), the
+//                start-bin skip (Q16) already applied in phase 1, and std::min/std::max NaN
+//                semantics (Q13) reproduced exactly: warps in which no lane can produce a NaN
+//                (no zero/NaN direction component) use FMNMX, the others the literal ternaries.
+//    Batches that do not fit the shared lists are split (fewer lights, then fewer steps of
+//    one light); the shadow state of a split light is carried between rounds.
+//  * Finished RGBA8 pixels are staged in shared memory and leave as 16-byte stores.
 // All fp32 arithmetic is IEEE round-to-nearest with no FMA contraction (-fmad=false).
 #include "par_kernels.cuh"
 
 namespace par {
 
-constexpr int kListCap = 1024;  // boxes per shared-memory window (2 x float4 each = 32 KB)
+constexpr int kListCap = 1024;   // boxes in the shared list (lo/hi float4 pairs = 32 KB)
+constexpr int kHashSize = 2048;  // de-duplication set, >= 2 x kListCap
+constexpr int kOccCap = 1024;    // occupied probed bins per round
+constexpr int kSegMax = 16;      // (light, step range) segments per round
+constexpr int kRun = 8;          // walk steps per phase-1 thread
+constexpr int kTilePixels = kBin * kBin;
 constexpr int kNoGroup = 0x7fffffff;
+constexpr unsigned kEmpty = 0xffffffffu;
+constexpr int kWarps = kTileThreads / 32;
 
-// alternative.cpp:40-83 on a box given as float lo/hi corners.  (float)(int - int) of
-// 16-bit operands equals the float difference exactly, so the int subtract + convert of the
-// reference is one FADD here.
-__device__ __forceinline__ bool slab_hit(const float4 lo, const float4 hi, float ox, float oy,
-                                         float oz, float ix, float iy, float iz) {
+struct Segment {
+    float sx, sy, sz;  // bin_step_size (alternative.cpp:423-425)
+    int light;         // index into ShadeParams::lights
+    int steps;         // (int)largest_bin_distance of the whole walk
+    int ka, kb;        // step range [ka, kb) covered by this segment
+    int item0;         // first phase-1 work item
+    int count;         // boxes found (before de-duplication)
+    int base;          // first slot of the segment in the box list
+    int fill;          // boxes stored (after de-duplication)
+    int pad;
+};
+
+struct ShadeSmem {
+    float4 list[2 * kListCap];
+    unsigned hash[kHashSize];
+    uint2 occ[kOccCap];  // .x = flat bin, .y = segment << 8 | count
+    float acc[kTilePixels];
+    unsigned out[kTilePixels];
+    unsigned short pix[kTilePixels];
+    unsigned char sh[kTilePixels];
+    Segment seg[kSegMax];
+    int warp_scan[kWarps];
+    int scan_total;
+    int group;
+    int n_occ;
+    int n_items;
+    int n_fit;
+    int decision;  // 0 = go, 1 = retry
+};
+
+// alternative.cpp:40-83, literal std::min/std::max (valid for every input, NaN included).
+__device__ __forceinline__ bool slab_hit_exact(const float4 lo, const float4 hi, float ox, float oy,
+                                               float oz, float ix, float iy, float iz) {
+    // (float)(int - int) of 16-bit operands equals the float difference exactly, so the
+    // reference's int subtract + convert is one FADD here.
     float x1 = (lo.x - ox) * ix, x2 = (hi.x - ox) * ix;
     float tmin = std_min(x1, x2);
     float tmax = std_max(x1, x2);
@@ -43,8 +89,33 @@ __device__ __forceinline__ bool slab_hit(const float4 lo, const float4 hi, float
     return tmax >= tmin;
 }
 
-// Block-wide exclusive scan of one int per thread (blockDim = kTileThreads = 10 warps).
-__device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* s_total) {
+// Same test when no operand can be NaN (finite non-zero direction => finite products): then
+// std::min/std::max and fminf/fmaxf agree up to the sign of zero, which no comparison sees.
+__device__ __forceinline__ bool slab_hit_fast(const float4 lo, const float4 hi, float ox, float oy,
+                                              float oz, float ix, float iy, float iz) {
+    float x1 = (lo.x - ox) * ix, x2 = (hi.x - ox) * ix;
+    float y1 = (lo.y - oy) * iy, y2 = (hi.y - oy) * iy;
+    float z1 = (lo.z - oz) * iz, z2 = (hi.z - oz) * iz;
+    float tmin = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    return tmax >= tmin;
+}
+
+template <bool kExact>
+__device__ __forceinline__ bool any_box_hit(const float4* __restrict__ boxes, int n, int self,
+                                            float ox, float oy, float oz, float ix, float iy,
+                                            float iz) {
+    for (int e = 0; e < n; e++) {
+        const float4 lo = boxes[2 * e], hi = boxes[2 * e + 1];
+        const bool hit = kExact ? slab_hit_exact(lo, hi, ox, oy, oz, ix, iy, iz)
+                                : slab_hit_fast(lo, hi, ox, oy, oz, ix, iy, iz);
+        if (hit && __float_as_int(lo.w) != self) return true;  // quirk Q17: own entity never shadows
+    }
+    return false;
+}
+
+// Block-wide exclusive scan of one int per thread (10 warps); *total gets the sum.
+__device__ __forceinline__ int block_exclusive_scan(int v, ShadeSmem& s) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int incl = v;
 #pragma unroll
@@ -52,119 +123,156 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* s_warp, int* s_t
         int t = __shfl_up_sync(0xffffffffu, incl, o);
         if (lane >= o) incl += t;
     }
-    if (lane == 31) s_warp[w] = incl;
+    if (lane == 31) s.warp_scan[w] = incl;
     __syncthreads();
     if (threadIdx.x < 32) {
-        int x = threadIdx.x < kTileThreads / 32 ? s_warp[threadIdx.x] : 0;
+        int x = threadIdx.x < kWarps ? s.warp_scan[threadIdx.x] : 0;
         int xi = x;
 #pragma unroll
         for (int o = 1; o < 16; o <<= 1) {
             int t = __shfl_up_sync(0xffffffffu, xi, o);
             if (lane >= o) xi += t;
         }
-        if (threadIdx.x < kTileThreads / 32) s_warp[threadIdx.x] = xi - x;
-        if (threadIdx.x == kTileThreads / 32 - 1) *s_total = xi;
+        if (threadIdx.x < kWarps) s.warp_scan[threadIdx.x] = xi - x;
+        if (threadIdx.x == kWarps - 1) s.scan_total = xi;
     }
     __syncthreads();
-    return s_warp[w] + incl - v;
+    return s.warp_scan[w] + incl - v;
+}
+
+__device__ __forceinline__ unsigned quantise(uchar4 c, float f) {  // sprites.hpp:8-16
+    const unsigned r = (unsigned char)((float)c.x * f);
+    const unsigned g = (unsigned char)((float)c.y * f);
+    const unsigned b = (unsigned char)((float)c.z * f);
+    return r | g << 8 | b << 16 | (unsigned)c.w << 24;
 }
 
 __global__ void __launch_bounds__(kTileThreads, 3)
 k_shade(const __grid_constant__ ShadeParams p) {
-    __shared__ float4 s_lo[kListCap];  // box min corner; .w carries the entity index bits
-    __shared__ float4 s_hi[kListCap];  // box max corner
-    __shared__ int s_warp[kTileThreads / 32];
-    __shared__ int s_total;
-    __shared__ int s_group;
-    __shared__ float s_seed[3];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ShadeSmem& s = *reinterpret_cast<ShadeSmem*>(smem_raw);
 
     const ViewDims& d = p.d;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     const int bx = blockIdx.x % d.HW;
     const int ty = p.tile_row_first + blockIdx.x / d.HW;
-    const int col = tid % kBin, rsub = tid / kBin;
-    const int i = bx * kBin + col;
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
+    const int n_lights = p.n_lights;
 
-    // Per-thread pixel state: 5 pixels of one column, 8 rows apart.
-    int gz[kTileRowsPerThread];     // start bin z of the pixel = world z / 40, kNoGroup for none
-    float acc[kTileRowsPerThread];  // running sum of Lambert terms of the visible lights
+    // ---- load the tile: start-bin z ("group") of every hit pixel; miss pixels are final ----
+    int gz[kTileRowsPerThread];
 #pragma unroll
     for (int m = 0; m < kTileRowsPerThread; m++) {
-        const int j = ty * kBin + rsub + 8 * m;
+        const int pidx = m * kTileThreads + tid;  // pixel (row pidx / 40, column pidx % 40) of the tile
+        const int j = ty * kBin + pidx / kBin;
         gz[m] = kNoGroup;
-        acc[m] = 0.f;
         if (j >= ra && j < rb) {
-            const int4 g = p.gbuf[(size_t)j * d.W + i];
-            if (g.w >= 0) gz[m] = g.z / kBin;  // ray_bin_z, alternative.cpp:727
+            const int4 g = p.gbuf[(size_t)j * d.W + bx * kBin + pidx % kBin];
+            if (g.w >= 0 && n_lights > 0) {
+                gz[m] = g.z / kBin;  // ray_bin_z, alternative.cpp:727
+            } else {
+                uchar4 c = make_uchar4(127, 127, 127, 0);  // miss colour, alternative.cpp:281
+                if (g.w >= 0) c = p.palette[p.atlas_color[(g.w >> 10) * kTexels + (g.w & 1023)]];
+                s.out[pidx] = quantise(c, std_min(1.f, 0.f + p.ambient));
+            }
         }
     }
 
     int last_group = -0x7fffffff - 1;
     for (;;) {
         // ---- next group: the smallest start-bin z not yet processed in this tile ----
-        if (tid == 0) s_group = kNoGroup;
+        if (tid == 0) s.group = kNoGroup;
         __syncthreads();
         int mine = kNoGroup;
 #pragma unroll
         for (int m = 0; m < kTileRowsPerThread; m++)
             if (gz[m] > last_group) mine = min(mine, gz[m]);
-        mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 16));
-        mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 8));
-        mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 4));
-        mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 2));
-        mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, 1));
-        if ((tid & 31) == 0 && mine != kNoGroup) atomicMin(&s_group, mine);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+        if (lane == 0 && mine != kNoGroup) atomicMin(&s.group, mine);
         __syncthreads();
-        const int group = s_group;
+        const int group = s.group;
         if (group == kNoGroup) break;
         last_group = group;
+
+        // ---- compact the group's pixels into a dense list ----
+        int my_n = 0;
+#pragma unroll
+        for (int m = 0; m < kTileRowsPerThread; m++) my_n += (gz[m] == group);
+        int pos = block_exclusive_scan(my_n, s);
+        const int npix = s.scan_total;
+#pragma unroll
+        for (int m = 0; m < kTileRowsPerThread; m++)
+            if (gz[m] == group) s.pix[pos++] = (unsigned short)(m * kTileThreads + tid);
 
         // start bin of every pixel of the group (alternative.cpp:724-727, quirk Q11)
         const int start = flat_bin(d, bx, ty, group);
 
-        for (int l = 0; l < p.n_lights; l++) {
-            const short4 lt = p.lights[l];
-            // light bin, alternative.cpp:729-732 ('/' truncates toward zero)
-            const int lbx = lt.x / kBin, lby = (d.H - lt.y - lt.z) / kBin, lbz = lt.z / kBin;
-            // walk set-up, alternative.cpp:406-430
-            const float dx = (float)lbx - (float)bx, dy = (float)lby - (float)ty,
-                        dz = (float)lbz - (float)group;
-            const float big = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-            const int steps = (int)big;  // 0 when big < 1 (and the NaN steps are never used)
-            const float stx = dx / big, sty = dy / big, stz = dz / big;
-
-            unsigned shadowed = 0;  // bit m: pixel m already found an occluder for this light
-            if (tid == 0) {
-                s_seed[0] = (float)bx;
-                s_seed[1] = (float)ty;
-                s_seed[2] = (float)group;
+        // ---- rounds over (light, step range) segments ----
+        int l_cur = 0, ka_cur = 0;  // next unprocessed step of light l_cur
+        int kb_try = -1;            // trial end of segment 0 (-1 = the whole walk)
+        int nseg_try = kSegMax;
+        bool fresh = true;          // first round of the group: acc starts at 0
+        while (l_cur < n_lights) {
+            // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
+            __syncthreads();  // previous round fully consumed (lists, segments, pix list complete)
+            if (tid < nseg_try && l_cur + tid < n_lights) {
+                const short4 lt = p.lights[l_cur + tid];
+                // light bin, alternative.cpp:729-732 ('/' truncates toward zero)
+                const int lbx = lt.x / kBin, lby = (d.H - lt.y - lt.z) / kBin, lbz = lt.z / kBin;
+                const float dx = (float)lbx - (float)bx, dy = (float)lby - (float)ty,
+                            dz = (float)lbz - (float)group;
+                const float big = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+                Segment& g = s.seg[tid];
+                g.steps = (int)big;  // 0 when big < 1 (then the NaN step is never used)
+                g.sx = dx / big;
+                g.sy = dy / big;
+                g.sz = dz / big;
+                g.light = l_cur + tid;
+                g.ka = tid == 0 ? ka_cur : 0;
+                g.kb = (tid == 0 && kb_try >= 0) ? kb_try : g.steps;
+                g.count = 0;
+                g.fill = 0;
             }
-            // chunks of blockDim steps (one step per thread); almost always exactly one
-            for (int chunk0 = 0; chunk0 == 0 || chunk0 < steps; chunk0 += kTileThreads) {
-                __syncthreads();
-                // ---- P1: this thread's step: positions, distinct probed bins, entry counts ----
-                const int k = chunk0 + tid;
-                unsigned probe[7];
-                int n_probe = 0, my_entries = 0;
-                float qx = 0.f, qy = 0.f, qz = 0.f;
-                if (k < steps) {
-                    // sequential fp32 accumulation from the chunk seed (quirk Q15)
-                    float px = s_seed[0], py = s_seed[1], pz = s_seed[2];
-                    for (int s = 0; s < tid; s++) {
-                        px = px + stx;
-                        py = py + sty;
-                        pz = pz + stz;
-                    }
-                    qx = px + stx;
-                    qy = py + sty;
-                    qz = pz + stz;
-                    const int x0 = (int)px, y0 = (int)py, z0 = (int)pz;
-                    const int x1 = (int)qx, y1 = (int)qy, z1 = (int)qz;
+            for (int i = tid; i < kHashSize; i += kTileThreads) s.hash[i] = kEmpty;
+            __syncthreads();
+            const int nseg = min(nseg_try, n_lights - l_cur);
+            if (tid == 0) {
+                int items = 0;
+                for (int q = 0; q < nseg; q++) {
+                    s.seg[q].item0 = items;
+                    items += (s.seg[q].kb - s.seg[q].ka + kRun - 1) / kRun;
+                }
+                s.n_items = items;
+                s.n_occ = 0;
+            }
+            __syncthreads();
+
+            // C. phase 1: walk.  One thread per run of kRun steps of one segment.
+            const int n_items = s.n_items;
+            for (int it = tid; it < n_items; it += kTileThreads) {
+                int q = 0;
+                while (q + 1 < nseg && s.seg[q + 1].item0 <= it) q++;
+                const Segment& g = s.seg[q];
+                const int k0 = g.ka + (it - g.item0) * kRun, k1 = min(k0 + kRun, g.kb);
+                const float sx = g.sx, sy = g.sy, sz = g.sz;
+                // sequential fp32 accumulation from the start bin (quirk Q15)
+                float px = (float)bx, py = (float)ty, pz = (float)group;
+                for (int k = 0; k < k0; k++) {
+                    px = px + sx;
+                    py = py + sy;
+                    pz = pz + sz;
+                }
+                int x0 = (int)px, y0 = (int)py, z0 = (int)pz;
+                for (int k = k0; k < k1; k++) {
+                    px = px + sx;
+                    py = py + sy;
+                    pz = pz + sz;
+                    const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
                     const int cx = x1 != x0, cy = y1 != y0, cz = z1 != z0;
-                    // The 7 probes of the step are the bins {x0|x1} x {y0|y1} x {z0|z1} minus
-                    // "all old"; the all-old bin was the previous step's last probe (or the
-                    // start bin, which is skipped anyway: quirk Q16).
+                    // The 7 probes of a step are the bins {x0|x1} x {y0|y1} x {z0|z1} minus "all
+                    // old"; the all-old bin was the previous step's last probe (or the start
+                    // bin, which is skipped anyway: quirk Q16).
 #pragma unroll
                     for (int mask = 1; mask < 8; mask++) {
                         if (((mask & 1) && !cx) || ((mask & 2) && !cy) || ((mask & 4) && !cz))
@@ -172,113 +280,178 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         const int f = flat_bin(d, (mask & 1) ? x1 : x0, (mask & 2) ? y1 : y0,
                                                (mask & 4) ? z1 : z0);
                         if (f == start || f < 0 || f >= d.V) continue;  // Q16 / Q18
-                        const int c = p.cnt[f] & (kSlots - 1);
-                        if (c) {
-                            probe[n_probe++] = (unsigned)f << 3 | (unsigned)c;
-                            my_entries += c;
-                        }
+                        if (!(__ldg(&p.occ_mask[f >> 5]) >> (f & 31) & 1)) continue;  // empty bin
+                        const int o = atomicAdd(&s.n_occ, 1);
+                        if (o < kOccCap) s.occ[o] = make_uint2((unsigned)f, (unsigned)q << 8);
+                    }
+                    x0 = x1;
+                    y0 = y1;
+                    z0 = z1;
+                }
+            }
+            __syncthreads();
+            // phase 1b: counts of the occupied bins
+            const int n_occ_all = s.n_occ, n_occ = min(n_occ_all, kOccCap);
+            for (int o = tid; o < n_occ; o += kTileThreads) {
+                const uint2 e = s.occ[o];
+                const int c = p.cnt[e.x] & (kSlots - 1);
+                s.occ[o].y = e.y | (unsigned)c;
+                atomicAdd(&s.seg[e.y >> 8].count, c);
+            }
+            __syncthreads();
+            // D. how many leading segments fit the box list?
+            if (tid == 0) {
+                int fit = 0, total = 0;
+                if (n_occ_all <= kOccCap) {
+                    while (fit < nseg && total + s.seg[fit].count <= kListCap) {
+                        s.seg[fit].base = total;
+                        total += s.seg[fit].count;
+                        fit++;
                     }
                 }
-                const int my_off = block_exclusive_scan(my_entries, s_warp, &s_total);
-                const int total = s_total;
-                if (tid == kTileThreads - 1 && k < steps) {  // seed of the next chunk
-                    s_seed[0] = qx;
-                    s_seed[1] = qy;
-                    s_seed[2] = qz;
+                s.n_fit = fit;
+            }
+            __syncthreads();
+            const int n_fit = s.n_fit;
+            if (n_fit == 0) {  // shrink: fewer lights first, then fewer steps of the first light
+                if (nseg_try > 1) {
+                    nseg_try = max(1, nseg / 2);
+                } else {
+                    const int ka = s.seg[0].ka, kb = s.seg[0].kb;
+                    kb_try = ka + max(1, (kb - ka) / 2);
                 }
-                const bool last_chunk = chunk0 + kTileThreads >= steps;
+                continue;
+            }
 
-                // ---- windows of at most kListCap boxes (almost always exactly one) ----
-                for (int w0 = 0; w0 == 0 || w0 < total; w0 += kListCap) {
-                    if (w0) __syncthreads();  // previous window fully consumed
-                    // P2: gather this thread's boxes that fall into the window
-                    int pos = my_off;
-                    for (int q = 0; q < n_probe; q++) {
-                        const int f = probe[q] >> 3, c = probe[q] & 7;
-                        for (int s = 0; s < c; s++, pos++) {
-                            if (pos < w0 || pos >= w0 + kListCap) continue;
-                            const int ent = p.ids[f * kSlots + s];
-                            const Box b = unpack_box(p.boxes[ent]);
-                            s_lo[pos - w0] = make_float4((float)b.px, (float)b.py, (float)b.pz,
-                                                         __int_as_float(ent));
-                            s_hi[pos - w0] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
-                                                         (float)(b.pz + b.ez), 0.f);
-                        }
+            // E. phase 2: gather + de-duplicate the boxes of the fitting segments
+            for (int idx = tid; idx < n_occ * kSlots; idx += kTileThreads) {
+                const uint2 e = s.occ[idx >> 3];
+                const int slot = idx & 7, c = e.y & 0xff, q = e.y >> 8;
+                if (slot >= c || q >= n_fit) continue;
+                const int ent = p.ids[e.x * kSlots + slot];
+                const unsigned key = (unsigned)q << 26 | (unsigned)ent;
+                unsigned h = (key * 2654435761u) >> 21;
+                bool fresh_key;
+                for (;;) {
+                    const unsigned old = atomicCAS(&s.hash[h], kEmpty, key);
+                    if (old == kEmpty || old == key) {
+                        fresh_key = old == kEmpty;
+                        break;
                     }
-                    __syncthreads();
-                    const int n = min(total - w0, kListCap);
-                    const bool last_window = last_chunk && (w0 + kListCap >= total);
+                    h = (h + 1) & (kHashSize - 1);
+                }
+                if (!fresh_key) continue;
+                const Box b = unpack_box(p.boxes[ent]);
+                const int at = s.seg[q].base + atomicAdd(&s.seg[q].fill, 1);
+                s.list[2 * at] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(ent));
+                s.list[2 * at + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
+                                                 (float)(b.pz + b.ez), 0.f);
+            }
+            __syncthreads();
 
-                    // ---- P3: per-pixel shading against the window ----
-#pragma unroll
-                    for (int m = 0; m < kTileRowsPerThread; m++) {
-                        if (gz[m] != group) continue;
-                        const int j = ty * kBin + rsub + 8 * m;
-                        const int4 g = p.gbuf[(size_t)j * d.W + i];
-                        const float* nrm = p.atlas_normal + ((g.w >> 10) * kTexels + (g.w & 1023)) * 3;
-                        const float nx = __ldg(nrm), ny = __ldg(nrm + 1), nz = __ldg(nrm + 2);
-                        // towards_light, L1-normalised (alternative.cpp:711-715, sprites.hpp:28-35)
-                        float tx = (float)(lt.x - i), tyv = (float)(lt.y - g.y), tz = (float)(lt.z - g.z);
-                        const float len = fabsf(tx) + fabsf(tyv) + fabsf(tz);
-                        tx = tx / len;
-                        tyv = tyv / len;
-                        tz = tz / len;
-                        // alternative.cpp:745-747
-                        const float lam = std_max(0.f, nx * tx + ny * tyv + nz * tz);
-                        if (!(lam > 0.f)) continue;  // quirk Q19: adds +0 whether visible or not
-                        if (!(shadowed >> m & 1) && n > 0) {
-                            // Ray, alternative.cpp:717-722
-                            const float ix = 1.f / tx, iy = 1.f / tyv, iz = 1.f / tz;
-                            const float ox = (float)(short)i, oy = (float)(short)g.y,
-                                        oz = (float)(short)g.z;
-                            bool hit = false;
-                            for (int e = 0; e < n; e++) {
-                                const float4 lo = s_lo[e];
-                                if (__float_as_int(lo.w) == g.x) continue;  // quirk Q17
-                                if (slab_hit(lo, s_hi[e], ox, oy, oz, ix, iy, iz)) {
-                                    hit = true;
-                                    break;
-                                }
-                            }
-                            if (hit) shadowed |= 1u << m;
-                        }
-                        if (last_window && !(shadowed >> m & 1)) acc[m] = acc[m] + lam;
+            // F. phase 3: one lane per pixel of the group
+            const bool final_round = s.seg[n_fit - 1].light == n_lights - 1 &&
+                                     s.seg[n_fit - 1].kb == s.seg[n_fit - 1].steps;
+            for (int qb = tid - lane; qb < npix; qb += kTileThreads) {
+                const int qi = qb + lane;
+                const bool valid = qi < npix;
+                const int pidx = valid ? s.pix[qi] : 0;
+                const int j = ty * kBin + pidx / kBin, i = bx * kBin + pidx % kBin;
+                int4 g = make_int4(0, 0, 0, 0);
+                float nx = 0.f, ny = 0.f, nz = 0.f, acc = 0.f;
+                bool shadowed = false;
+                if (valid) {
+                    g = p.gbuf[(size_t)j * d.W + i];
+                    const float* nrm = p.atlas_normal + ((g.w >> 10) * kTexels + (g.w & 1023)) * 3;
+                    nx = __ldg(nrm);
+                    ny = __ldg(nrm + 1);
+                    nz = __ldg(nrm + 2);
+                    if (!fresh) acc = s.acc[qi];
+                    shadowed = s.sh[qi] != 0;  // only meaningful when segment 0 continues a light
+                }
+                // Ray origin, alternative.cpp:720-722
+                const float ox = (float)(short)i, oy = (float)(short)g.y, oz = (float)(short)g.z;
+                for (int q = 0; q < n_fit; q++) {
+                    const Segment& sg = s.seg[q];
+                    const short4 lt = p.lights[sg.light];
+                    if (sg.ka == 0) shadowed = false;
+                    // towards_light, L1-normalised (alternative.cpp:711-715, sprites.hpp:28-35)
+                    float tx = (float)(lt.x - i), tyv = (float)(lt.y - g.y), tz = (float)(lt.z - g.z);
+                    const float len = fabsf(tx) + fabsf(tyv) + fabsf(tz);
+                    tx = tx / len;
+                    tyv = tyv / len;
+                    tz = tz / len;
+                    // alternative.cpp:745-747; a term of 0 adds +0 whether visible or not (Q19)
+                    const float lam = std_max(0.f, nx * tx + ny * tyv + nz * tz);
+                    const bool lit_candidate = valid && lam > 0.f;
+                    const int n = sg.fill;
+                    const bool test = lit_candidate && !shadowed && n > 0;
+                    // direction_inverse, alternative.cpp:717-719 (only needed when testing)
+                    float ix = 0.f, iy = 0.f, iz = 0.f;
+                    if (test) {
+                        ix = 1.f / tx;
+                        iy = 1.f / tyv;
+                        iz = 1.f / tz;
+                    }
+                    // a NaN can only arise from a zero (or NaN) direction component (quirk Q13)
+                    const bool nan_free = fabsf(tx) > 0.f && fabsf(tyv) > 0.f && fabsf(tz) > 0.f;
+                    const float4* boxes = s.list + 2 * sg.base;
+                    if (__any_sync(0xffffffffu, test && !nan_free)) {
+                        if (test && any_box_hit<true>(boxes, n, g.x, ox, oy, oz, ix, iy, iz)) shadowed = true;
+                    } else {
+                        if (test && any_box_hit<false>(boxes, n, g.x, ox, oy, oz, ix, iy, iz)) shadowed = true;
+                    }
+                    if (sg.kb == sg.steps && lit_candidate && !shadowed) acc = acc + lam;
+                }
+                if (valid) {
+                    if (final_round) {
+                        const uchar4 c = p.palette[p.atlas_color[(g.w >> 10) * kTexels + (g.w & 1023)]];
+                        // alternative.cpp:735 / 757-758
+                        s.out[pidx] = quantise(c, std_min(1.f, acc + p.ambient));
+                    } else {
+                        s.acc[qi] = acc;
+                        s.sh[qi] = shadowed;
                     }
                 }
             }
+
+            // advance past the processed segments
+            const Segment& last = s.seg[n_fit - 1];
+            if (last.kb == last.steps) {
+                l_cur = last.light + 1;
+                ka_cur = 0;
+            } else {  // a split light: n_fit == 1
+                l_cur = last.light;
+                ka_cur = last.kb;
+            }
+            kb_try = -1;
+            nseg_try = kSegMax;
+            fresh = false;
         }
     }
 
-    // ---- quantise + pack + 16-byte stores (alternative.cpp:735/757-758, sprites.hpp:8-16) ----
-#pragma unroll
-    for (int m = 0; m < kTileRowsPerThread; m++) {
-        const int j = ty * kBin + rsub + 8 * m;
-        const bool valid = j >= ra && j < rb;  // uniform across the 4 lanes of a quad
-        unsigned rgba = 0;
-        if (valid) {
-            const int4 g = p.gbuf[(size_t)j * d.W + i];
-            uchar4 c = make_uchar4(127, 127, 127, 0);  // miss colour, alternative.cpp:281
-            if (g.w >= 0) c = p.palette[p.atlas_color[(g.w >> 10) * kTexels + (g.w & 1023)]];
-            const float f = std_min(1.f, acc[m] + p.ambient);
-            const unsigned r = (unsigned char)((float)c.x * f);
-            const unsigned gg = (unsigned char)((float)c.y * f);
-            const unsigned b = (unsigned char)((float)c.z * f);
-            rgba = r | gg << 8 | b << 16 | (unsigned)c.w << 24;
-        }
-        // lanes 4q..4q+3 hold 4 consecutive pixels of one row (40 and 32 are multiples of 4)
-        const unsigned v1 = __shfl_down_sync(0xffffffffu, rgba, 1);
-        const unsigned v2 = __shfl_down_sync(0xffffffffu, rgba, 2);
-        const unsigned v3 = __shfl_down_sync(0xffffffffu, rgba, 3);
-        if (valid && (tid & 3) == 0)
-            *reinterpret_cast<uint4*>(&p.out[(size_t)j * d.W + i]) = make_uint4(rgba, v1, v2, v3);
+    // ---- 16-byte stores of the finished tile rows ----
+    __syncthreads();
+    for (int v = tid; v < kTilePixels / 4; v += kTileThreads) {
+        const int j = ty * kBin + v / (kBin / 4);
+        if (j < ra || j >= rb) continue;
+        const uint4 px = *reinterpret_cast<const uint4*>(&s.out[4 * v]);
+        *reinterpret_cast<uint4*>(&p.out[(size_t)j * d.W + bx * kBin + 4 * (v % (kBin / 4))]) = px;
     }
 }
 
-cudaError_t launch_shade(const ShadeParams& p, cudaStream_t s) {
+size_t shade_smem_bytes() { return sizeof(ShadeSmem); }
+
+cudaError_t configure_shade() {
+    return cudaFuncSetAttribute(k_shade, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)sizeof(ShadeSmem));
+}
+
+cudaError_t launch_shade(const ShadeParams& p, cudaStream_t st) {
     const ViewDims& d = p.d;
     int tile_rows = (d.row1 + kBin - 1) / kBin - d.row0 / kBin;
     if (tile_rows <= 0) return cudaSuccess;
-    k_shade<<<tile_rows * d.HW, kTileThreads, 0, s>>>(p);
+    k_shade<<<tile_rows * d.HW, kTileThreads, sizeof(ShadeSmem), st>>>(p);
     return cudaGetLastError();
 }
 
