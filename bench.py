@@ -195,8 +195,8 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     W, H, L, desc, boxes, lights = make_workload(par, args.workload)
     n_lights = len(lights)
-    rows = H // world  # H/N is integral for every config
-    row0, row1 = rank * rows, (rank + 1) * rows if rank < world - 1 else H
+    from par_b200.bands import band_rows, gather_bands
+    row0, row1 = band_rows(H, world, rank)  # H/N is integral for every config
     rays_frame = W * H * (1 + n_lights)
 
     stream = torch.cuda.Stream(device=dev)
@@ -204,7 +204,6 @@ def ours(args):
     ren.set_stream(stream.cuda_stream)
     ren.set_atlas()
     frame = torch.zeros(H * W * 4, dtype=torch.uint8, device=dev)  # the full frame in HBM
-    band = frame[row0 * W * 4: row1 * W * 4]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     h_boxes = par.pinned_empty(len(boxes), par.AABB)
     h_boxes[:] = boxes
@@ -212,8 +211,7 @@ def ours(args):
     t_hframe = torch.from_numpy(h_frame.view(np.uint8).reshape(-1)) if rank == 0 else None
 
     def gather():
-        if world > 1:
-            dist.all_gather_into_tensor(frame, band)  # in place: band r lives at offset r of frame
+        gather_bands(frame, W, H, world, rank)  # in place: band r lives at offset r of frame
 
     def step_resident():
         ren.rebuild_grid()                       # device scene loader on the resident scene

@@ -118,6 +118,7 @@ const char* par_version(void);
 /* Use an external CUDA stream (cudaStream_t cast to void*) for all work of this context;
  * NULL restores the context's own stream.  Lets a host framework order and time the work. */
 int par_set_stream(par_ctx* ctx, void* cuda_stream);
+void* par_get_stream(par_ctx* ctx); /* the cudaStream_t all work of the context is ordered on */
 int par_sync(par_ctx* ctx);
 
 /* Pinned host memory for frame/scene buffers (optional; any host pointer is accepted). */
@@ -164,6 +165,23 @@ int par_get_gbuffer(par_ctx* ctx, par_pixel* gbuf, int32_t* texel);
 int par_get_grid(par_ctx* ctx, int32_t* count, int32_t* ids);
 int par_get_stats(par_ctx* ctx, par_stats* stats);
 int par_grid_volume(const par_ctx* ctx);
+
+/* -- single-process multi-GPU: row bands + in-place ncclAllGather of the frame over NVLink -- */
+/* One par_ctx per device renders rows [i*H/n, (i+1)*H/n) of the same scene (the scene and grid
+ * are replicated).  NCCL is loaded lazily with dlopen and only when n_devices > 1. */
+typedef struct par_multi par_multi;
+int par_multi_create(par_multi** out, const par_config* cfg, const int* devices, int n_devices);
+void par_multi_destroy(par_multi* m);
+int par_multi_size(const par_multi* m);
+par_ctx* par_multi_context(par_multi* m, int i); /* band i's context (G-buffer, stats, grid) */
+int par_multi_set_atlas(par_multi* m, const par_sprite* sprites, int n_sprites,
+                        const par_color* palette, int n_palette);
+int par_multi_set_scene(par_multi* m, const par_aabb* aabbs, const int32_t* sprite_ids, int n);
+/* Renders every band, gathers, and reads the finished frame back from device 0 into out_rgba
+ * (host, W*H; NULL = leave it in HBM, complete on every device).  Synchronous. */
+int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_color* out_rgba,
+                     par_stats* stats);
+const char* par_multi_last_error(void);
 
 /* -- host-side pieces of the reference that sit either side of the path ---------------- */
 /* make_tile_floor(), sprites.hpp:73-364, and color_palette, sprites.hpp:60-65. */

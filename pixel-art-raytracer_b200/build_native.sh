@@ -18,5 +18,9 @@ for src in "$here"/csrc/*.cu "$here"/host/host_scene.cpp; do
     fi
     objs+=("$obj")
 done
-"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${objs[@]}" -o "$out"
-echo "built $out"
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${objs[@]}" -o "$out" -ldl
+# headless C++ host: stand-in for the reference's main loop on top of the C ABI
+CXXB="$( [ -x /usr/bin/g++ ] && echo /usr/bin/g++ || echo g++ )"
+"$CXXB" -std=c++20 -O2 -I"$root/include" "$here/host/par_headless.cpp" -L"$here/par_b200" -lpar_b200 \
+    -Wl,-rpath,'$ORIGIN/../par_b200' -o "$here/build/par_headless"
+echo "built $out and $here/build/par_headless"

@@ -1,0 +1,207 @@
+// multi_gpu.cu — single-process multi-GPU mode of the C ABI (par_multi_*): the image is split
+// into row bands, one par_ctx per device renders its band in place into a full-size frame in
+// its own HBM, and one in-place ncclAllGather over NVLink completes the frame on every device
+// (SURVEY.md §8e).  The scene/grid is replicated: a shadow ray may visit any bin.
+//
+// NCCL is loaded lazily with dlopen("libnccl.so.2") so that libpar_b200.so itself has no
+// link-time NCCL dependency and the one-GPU path never touches it.  (bench.py's torchrun mode
+// does the same exchange with torch.distributed's NCCL, one process per GPU.)
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "par/par.h"
+#include "par_kernels.cuh"
+
+namespace {
+
+struct Nccl {
+    void* handle = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+
+    bool load() {
+        if (handle) return true;
+        handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+        if (!handle) return false;
+#define PAR_SYM(name) name = reinterpret_cast<decltype(name)>(dlsym(handle, "nccl" #name))
+        PAR_SYM(CommInitAll);
+        PAR_SYM(CommDestroy);
+        PAR_SYM(AllGather);
+        PAR_SYM(Broadcast);
+        PAR_SYM(GroupStart);
+        PAR_SYM(GroupEnd);
+        PAR_SYM(GetErrorString);
+#undef PAR_SYM
+        return CommInitAll && CommDestroy && AllGather && Broadcast && GroupStart && GroupEnd && GetErrorString;
+    }
+};
+
+Nccl g_nccl;
+thread_local char g_multi_err[256] = "";
+
+}  // namespace
+
+struct par_multi {
+    int n = 0;
+    int W = 0, H = 0;
+    par_ctx* ctx[8] = {};
+    int device[8] = {};
+    int row0[8] = {}, row1[8] = {};
+    ncclComm_t comm[8] = {};
+    bool have_comm = false;
+};
+
+extern "C" {
+
+const char* par_multi_last_error(void) { return g_multi_err[0] ? g_multi_err : par_last_error(); }
+
+void par_multi_destroy(par_multi* m) {
+    if (!m) return;
+    for (int i = 0; i < m->n; i++) {
+        if (m->have_comm && m->comm[i]) g_nccl.CommDestroy(m->comm[i]);
+        par_destroy(m->ctx[i]);
+    }
+    delete m;
+}
+
+int par_multi_create(par_multi** out, const par_config* cfg, const int* devices, int n_devices) {
+    g_multi_err[0] = 0;
+    if (!out || !cfg || !devices || n_devices < 1 || n_devices > 8 || cfg->height < n_devices) {
+        snprintf(g_multi_err, sizeof g_multi_err, "par_multi_create: bad argument (1..8 devices)");
+        return PAR_ERR_INVALID_ARG;
+    }
+    *out = nullptr;
+    par_multi* m = new (std::nothrow) par_multi;
+    if (!m) return PAR_ERR_OUT_OF_MEMORY;
+    m->n = n_devices;
+    m->W = cfg->width;
+    m->H = cfg->height;
+    const int rows = cfg->height / n_devices;
+    for (int i = 0; i < n_devices; i++) {
+        par_config c = *cfg;
+        c.device = devices[i];
+        c.row_begin = i * rows;
+        c.row_end = (i == n_devices - 1) ? cfg->height : (i + 1) * rows;
+        m->device[i] = devices[i];
+        m->row0[i] = c.row_begin;
+        m->row1[i] = c.row_end;
+        int rc = par_create(&m->ctx[i], &c);
+        if (rc != PAR_OK) {
+            par_multi_destroy(m);
+            return rc;
+        }
+    }
+    if (n_devices > 1) {
+        if (!g_nccl.load()) {
+            snprintf(g_multi_err, sizeof g_multi_err, "par_multi_create: cannot load libnccl.so.2: %s", dlerror());
+            par_multi_destroy(m);
+            return PAR_ERR_NCCL;
+        }
+        ncclResult_t r = g_nccl.CommInitAll(m->comm, n_devices, devices);
+        if (r != ncclSuccess) {
+            snprintf(g_multi_err, sizeof g_multi_err, "ncclCommInitAll: %s", g_nccl.GetErrorString(r));
+            par_multi_destroy(m);
+            return PAR_ERR_NCCL;
+        }
+        m->have_comm = true;
+    }
+    *out = m;
+    return PAR_OK;
+}
+
+int par_multi_size(const par_multi* m) { return m ? m->n : 0; }
+par_ctx* par_multi_context(par_multi* m, int i) { return (m && i >= 0 && i < m->n) ? m->ctx[i] : nullptr; }
+
+int par_multi_set_atlas(par_multi* m, const par_sprite* sprites, int n_sprites, const par_color* palette,
+                        int n_palette) {
+    if (!m) return PAR_ERR_INVALID_ARG;
+    for (int i = 0; i < m->n; i++) {
+        int rc = par_set_atlas(m->ctx[i], sprites, n_sprites, palette, n_palette);
+        if (rc != PAR_OK) return rc;
+    }
+    return PAR_OK;
+}
+
+int par_multi_set_scene(par_multi* m, const par_aabb* aabbs, const int32_t* sprite_ids, int n) {
+    if (!m) return PAR_ERR_INVALID_ARG;
+    for (int i = 0; i < m->n; i++) {  // asynchronous per device: uploads and loaders overlap
+        int rc = par_set_scene(m->ctx[i], aabbs, sprite_ids, n);
+        if (rc != PAR_OK) return rc;
+    }
+    return PAR_OK;
+}
+
+// Render all bands, gather, and (out_rgba != NULL) read the finished frame back from device 0.
+int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_color* out_rgba, par_stats* stats) {
+    g_multi_err[0] = 0;
+    if (!m) return PAR_ERR_INVALID_ARG;
+    for (int i = 0; i < m->n; i++) {
+        int rc = par_render_device(m->ctx[i], lights, n_lights, nullptr);
+        if (rc != PAR_OK) return rc;
+    }
+    if (m->n > 1) {
+        const size_t row_bytes = (size_t)m->W * 4;
+        const bool equal = m->H % m->n == 0;
+        ncclResult_t r = g_nccl.GroupStart();
+        for (int i = 0; i < m->n && r == ncclSuccess; i++) {
+            unsigned char* frame = static_cast<unsigned char*>(par_device_frame(m->ctx[i]));
+            cudaStream_t st = static_cast<cudaStream_t>(par_get_stream(m->ctx[i]));
+            if (equal) {  // in place: band i lives at offset i of every frame
+                r = g_nccl.AllGather(frame + m->row0[i] * row_bytes, frame, (m->row1[i] - m->row0[i]) * row_bytes,
+                                     ncclUint8, m->comm[i], st);
+            } else {
+                for (int b = 0; b < m->n && r == ncclSuccess; b++)
+                    r = g_nccl.Broadcast(frame + m->row0[b] * row_bytes, frame + m->row0[b] * row_bytes,
+                                         (m->row1[b] - m->row0[b]) * row_bytes, ncclUint8, b, m->comm[i], st);
+            }
+        }
+        ncclResult_t e = g_nccl.GroupEnd();
+        if (r == ncclSuccess) r = e;
+        if (r != ncclSuccess) {
+            snprintf(g_multi_err, sizeof g_multi_err, "NCCL frame gather: %s", g_nccl.GetErrorString(r));
+            return PAR_ERR_NCCL;
+        }
+    }
+    if (out_rgba) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(m->device[0]);
+        cudaError_t ce = cudaMemcpyAsync(out_rgba, par_device_frame(m->ctx[0]), (size_t)m->W * m->H * 4,
+                                         cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(par_get_stream(m->ctx[0])));
+        cudaSetDevice(prev);
+        if (ce != cudaSuccess) {
+            snprintf(g_multi_err, sizeof g_multi_err, "frame readback: %s", cudaGetErrorString(ce));
+            return PAR_ERR_CUDA;
+        }
+    }
+    for (int i = 0; i < m->n; i++) {
+        int rc = par_sync(m->ctx[i]);
+        if (rc != PAR_OK) return rc;
+    }
+    if (stats) {
+        int rc = par_get_stats(m->ctx[0], stats);
+        if (rc != PAR_OK) return rc;
+        for (int i = 1; i < m->n; i++) {  // the frame is done when the slowest band is
+            par_stats s;
+            if (par_get_stats(m->ctx[i], &s) != PAR_OK) continue;
+            if (s.ms_total > stats->ms_total) stats->ms_total = s.ms_total;
+            if (s.ms_shade > stats->ms_shade) stats->ms_shade = s.ms_shade;
+            if (s.ms_primary > stats->ms_primary) stats->ms_primary = s.ms_primary;
+            stats->kernel_launches += s.kernel_launches;
+            stats->rays += s.rays;
+        }
+    }
+    return PAR_OK;
+}
+
+}  // extern "C"

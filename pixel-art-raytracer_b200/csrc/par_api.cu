@@ -256,6 +256,8 @@ int par_set_stream(par_ctx* c, void* cuda_stream) {
     return PAR_OK;
 }
 
+void* par_get_stream(par_ctx* c) { return c ? static_cast<void*>(c->stream) : nullptr; }
+
 int par_sync(par_ctx* c) {
     if (!c) return fail(PAR_ERR_INVALID_ARG, "par_sync: null context%s%s");
     DeviceGuard guard(c->cfg.device);

@@ -33,7 +33,9 @@ STATUS_NAMES = {0: "PAR_OK", -1: "PAR_ERR_INVALID_ARG", -2: "PAR_ERR_NO_DEVICE",
 
 # every symbol include/par/par.h declares (checked by tests/test_abi.py)
 EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_set_stream",
-           "par_sync", "par_alloc_host", "par_free_host", "par_set_atlas", "par_set_scene",
+           "par_get_stream", "par_multi_create", "par_multi_destroy", "par_multi_size",
+           "par_multi_context", "par_multi_set_atlas", "par_multi_set_scene", "par_multi_render",
+           "par_multi_last_error", "par_sync", "par_alloc_host", "par_free_host", "par_set_atlas", "par_set_scene",
            "par_rebuild_grid", "par_render", "par_render_device", "par_device_frame",
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
@@ -81,6 +83,18 @@ def lib():
         L.par_version.restype = C.c_char_p
         L.par_set_stream.argtypes = [vp, vp]
         L.par_sync.argtypes = [vp]
+        L.par_get_stream.argtypes = [vp]
+        L.par_get_stream.restype = vp
+        L.par_multi_create.argtypes = [C.POINTER(vp), C.POINTER(Config), C.POINTER(C.c_int), i32]
+        L.par_multi_destroy.argtypes = [vp]
+        L.par_multi_destroy.restype = None
+        L.par_multi_size.argtypes = [vp]
+        L.par_multi_context.argtypes = [vp, i32]
+        L.par_multi_context.restype = vp
+        L.par_multi_set_atlas.argtypes = [vp, vp, i32, vp, i32]
+        L.par_multi_set_scene.argtypes = [vp, vp, vp, i32]
+        L.par_multi_render.argtypes = [vp, vp, i32, vp, C.POINTER(Stats)]
+        L.par_multi_last_error.restype = C.c_char_p
         L.par_alloc_host.argtypes = [C.c_size_t]
         L.par_alloc_host.restype = vp
         L.par_free_host.argtypes = [vp]
@@ -271,3 +285,55 @@ class Renderer:
         st = Stats()
         _check(lib().par_get_stats(self._h, C.byref(st)))
         return st.as_dict()
+
+
+class MultiRenderer:
+    """par_multi_*: one process, N GPUs, row bands + in-place ncclAllGather of the frame."""
+
+    def __init__(self, W, H, L, devices):
+        self.W, self.H, self.L = W, H, L
+        self._h = C.c_void_p()
+        cfg = Config(W, H, L, 0, 0, 0, 0.0)
+        devs = (C.c_int * len(devices))(*devices)
+        rc = lib().par_multi_create(C.byref(self._h), C.byref(cfg), devs, len(devices))
+        if rc != PAR_OK:
+            raise ParError(rc, lib().par_multi_last_error().decode())
+
+    def _check(self, rc):
+        if rc != PAR_OK:
+            raise ParError(rc, lib().par_multi_last_error().decode())
+
+    def close(self):
+        if self._h:
+            lib().par_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_atlas(self, sprites=None, palette=None):
+        sprites = tile_floor() if sprites is None else np.ascontiguousarray(sprites, SPRITE)
+        palette = default_palette() if palette is None else np.ascontiguousarray(palette, COLOR)
+        self._check(lib().par_multi_set_atlas(self._h, _p(sprites), len(sprites), _p(palette), len(palette)))
+
+    def set_scene(self, aabbs, sprite_ids=None):
+        aabbs = np.ascontiguousarray(aabbs, AABB)
+        if sprite_ids is not None:
+            sprite_ids = np.ascontiguousarray(sprite_ids, np.int32)
+        self._check(lib().par_multi_set_scene(self._h, _p(aabbs), _p(sprite_ids), len(aabbs)))
+
+    def render(self, lights, out=None):
+        lights = np.ascontiguousarray(lights, LIGHT)
+        rgba = np.zeros((self.H, self.W), COLOR) if out is None else out
+        st = Stats()
+        self._check(lib().par_multi_render(self._h, _p(lights), len(lights), _p(rgba), C.byref(st)))
+        return rgba, st.as_dict()

@@ -1,0 +1,52 @@
+"""Host logic of the multi-GPU mode on CPU: world_size-2 (and 3, unequal bands) gloo process
+groups; every rank fills its row band from the oracle and the in-place gather must give the
+full oracle frame on every rank."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG, ROOT
+
+
+def _worker(rank, world, port, W, H, L, out_dir):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from par_b200.bands import band_rows, gather_bands
+    boxes, lights = O.scene_synthetic(W, H, L, n=600, n_lights=3)
+    r0, r1 = band_rows(H, world, rank)
+    band = O.render(W, H, L, boxes, lights, row0=r0, row1=r1, want_gbuf=False, want_texel=False)["rgba"]
+    frame = torch.from_numpy(band.view(np.uint8).reshape(-1).copy())
+    assert not frame[: r0 * W * 4].any() and not frame[r1 * W * 4:].any()
+    gather_bands(frame, W, H, world, rank)
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), frame.numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,H", [(2, 320), (3, 320)])
+def test_band_gather(oracle, tmp_path, world, H):
+    W, L = 480, 320
+    port = 29500 + os.getpid() % 2000 + world
+    mp.spawn(_worker, args=(world, port, W, H, L, str(tmp_path)), nprocs=world, join=True)
+    boxes, lights = oracle.scene_synthetic(W, H, L, n=600, n_lights=3)
+    full = oracle.render(W, H, L, boxes, lights, want_gbuf=False, want_texel=False)["rgba"]
+    want = full.view(np.uint8).reshape(-1)
+    for r in range(world):
+        got = np.load(tmp_path / f"rank{r}.npy")
+        assert np.array_equal(got, want), f"rank {r}"
+
+
+def test_band_rows():
+    from par_b200.bands import band_rows
+    assert [band_rows(2160, 8, r) for r in (0, 7)] == [(0, 270), (1890, 2160)]
+    assert [band_rows(320, 3, r) for r in range(3)] == [(0, 106), (106, 212), (212, 320)]
+    assert band_rows(4320, 1, 0) == (0, 4320)
+    with pytest.raises(ValueError):
+        band_rows(320, 2, 2)
