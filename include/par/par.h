@@ -165,6 +165,9 @@ int par_get_gbuffer(par_ctx* ctx, par_pixel* gbuf, int32_t* texel);
 int par_get_grid(par_ctx* ctx, int32_t* count, int32_t* ids);
 int par_get_stats(par_ctx* ctx, par_stats* stats);
 int par_grid_volume(const par_ctx* ctx);
+/* Debug aid: barrier-to-barrier cycle totals of the shade kernel's phases (16 counters,
+ * summed over CTAs).  enable != 0 switches the instrumentation on and zeroes it. */
+int par_debug_phase_timing(par_ctx* ctx, int enable, uint64_t* out16);
 
 /* -- single-process multi-GPU: row bands + in-place ncclAllGather of the frame over NVLink -- */
 /* One par_ctx per device renders rows [i*H/n, (i+1)*H/n) of the same scene (the scene and grid

@@ -96,6 +96,7 @@ struct par_ctx {
     uchar4* d_frame = nullptr;
     int* d_expanded = nullptr;  // W*H*7 ints, lazily allocated
     int* d_texel = nullptr;     // W*H ints, lazily allocated
+    unsigned long long* d_phase_cycles = nullptr;  // debug only
     bool scene_set = false, frame_valid = false, build_timed = false, frame_timed = false;
     int launches_build = 0, launches_frame = 0, last_n_lights = 0;
     float ambient = 0.25f;
@@ -241,6 +242,7 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_frame);
     cudaFree(c->d_expanded);
     cudaFree(c->d_texel);
+    cudaFree(c->d_phase_cycles);
     cudaEvent_t evs[] = {c->ev_build0, c->ev_build1, c->ev_f0, c->ev_f1, c->ev_f2};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
@@ -415,7 +417,7 @@ int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d
     sp.n_lights = n_lights;
     sp.ambient = c->ambient;
     sp.tile_row_first = d.row0 / kBin;
-    sp.slab_counter = nullptr;
+    sp.phase_cycles = c->d_phase_cycles;  // NULL unless par_debug_phase_timing enabled it
     memset(sp.lights, 0, sizeof sp.lights);
     for (int l = 0; l < n_lights; l++)
         sp.lights[l] = make_short4(lights[l].x, lights[l].y, lights[l].z, lights[l].radius);
@@ -499,6 +501,27 @@ int par_get_gbuffer(par_ctx* c, par_pixel* gbuf, int32_t* texel) {
 }
 
 int par_grid_volume(const par_ctx* c) { return c ? c->d.V : 0; }
+
+// Debug: barrier-to-barrier cycle totals of k_shade's phases, summed over CTAs.  enable != 0
+// switches the instrumentation on (and zeroes the counters); out (16 values) may be NULL.
+int par_debug_phase_timing(par_ctx* c, int enable, uint64_t* out) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_debug_phase_timing: null context%s%s");
+    DeviceGuard guard(c->cfg.device);
+    PAR_CUDA(cudaStreamSynchronize(c->stream));
+    if (out) {
+        memset(out, 0, 16 * sizeof(uint64_t));
+        if (c->d_phase_cycles)
+            PAR_CUDA(cudaMemcpy(out, c->d_phase_cycles, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    }
+    if (enable) {
+        if (!c->d_phase_cycles) PAR_CUDA(cudaMalloc(&c->d_phase_cycles, 16 * sizeof(uint64_t)));
+        PAR_CUDA(cudaMemset(c->d_phase_cycles, 0, 16 * sizeof(uint64_t)));
+    } else if (c->d_phase_cycles) {
+        cudaFree(c->d_phase_cycles);
+        c->d_phase_cycles = nullptr;
+    }
+    return PAR_OK;
+}
 
 int par_get_grid(par_ctx* c, int32_t* count, int32_t* ids) {
     if (!c) return fail(PAR_ERR_INVALID_ARG, "par_get_grid: null context%s%s");

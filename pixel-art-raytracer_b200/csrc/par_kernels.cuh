@@ -48,7 +48,7 @@ struct ShadeParams {
     int n_lights;
     float ambient;
     int tile_row_first;
-    unsigned long long* slab_counter;  // optional instrumentation (NULL in production)
+    unsigned long long* phase_cycles;  // optional debug instrumentation: 16 counters (NULL in production)
     short4 lights[kMaxLights];         // x, y, z, radius (alternative.cpp:619-622)
 };
 size_t shade_smem_bytes();

@@ -32,15 +32,29 @@
 
 namespace par {
 
-constexpr int kListCap = 1024;   // boxes in the shared list (lo/hi float4 pairs = 32 KB)
-constexpr int kHashSize = 2048;  // de-duplication set, >= 2 x kListCap
-constexpr int kOccCap = 1024;    // occupied probed bins per round
-constexpr int kSegMax = 16;      // (light, step range) segments per round
-constexpr int kRun = 8;          // walk steps per phase-1 thread
+#ifndef PAR_SHADE_THREADS
+#define PAR_SHADE_THREADS 160
+#endif
+#ifndef PAR_SHADE_LIST_CAP
+#define PAR_SHADE_LIST_CAP 512
+#endif
+#ifndef PAR_SHADE_MIN_CTAS
+#define PAR_SHADE_MIN_CTAS 6
+#endif
+constexpr int kThreads = PAR_SHADE_THREADS;   // CTA size of k_shade (a multiple of 32 dividing 1600)
+constexpr int kListCap = PAR_SHADE_LIST_CAP;  // boxes in the shared list (lo/hi float4 pairs, 32 B each)
+constexpr int kHashSize = 2 * kListCap;       // de-duplication set
+constexpr int kHashBits = kListCap == 1024 ? 11 : kListCap == 512 ? 10 : 9;
+constexpr int kOccCap = kListCap;             // occupied probed bins per round
+constexpr int kSegMax = 16;                   // (light, step range) segments per round
+constexpr int kMaxRun = 16;                   // most walk steps per phase-1 thread
 constexpr int kTilePixels = kBin * kBin;
+constexpr int kPixPerThread = kTilePixels / kThreads;
 constexpr int kNoGroup = 0x7fffffff;
 constexpr unsigned kEmpty = 0xffffffffu;
-constexpr int kWarps = kTileThreads / 32;
+constexpr int kWarps = kThreads / 32;
+static_assert(kTilePixels % kThreads == 0 && kThreads % 32 == 0 && kWarps <= 16, "CTA size");
+static_assert((1 << kHashBits) == kHashSize, "hash size");
 
 struct Segment {
     float sx, sy, sz;  // bin_step_size (alternative.cpp:423-425)
@@ -58,8 +72,7 @@ struct ShadeSmem {
     float4 list[2 * kListCap];
     unsigned hash[kHashSize];
     uint2 occ[kOccCap];  // .x = flat bin, .y = segment << 8 | count
-    float acc[kTilePixels];
-    unsigned out[kTilePixels];
+    unsigned out[kTilePixels];  // finished RGBA8; between rounds of a split group: the fp32 acc bits
     unsigned short pix[kTilePixels];
     unsigned char sh[kTilePixels];
     Segment seg[kSegMax];
@@ -68,8 +81,7 @@ struct ShadeSmem {
     int group;
     int n_occ;
     int n_items;
-    int n_fit;
-    int decision;  // 0 = go, 1 = retry
+    int run;  // walk steps per phase-1 thread this round
 };
 
 // alternative.cpp:40-83, literal std::min/std::max (valid for every input, NaN included).
@@ -147,7 +159,7 @@ __device__ __forceinline__ unsigned quantise(uchar4 c, float f) {  // sprites.hp
     return r | g << 8 | b << 16 | (unsigned)c.w << 24;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 3)
+__global__ void __launch_bounds__(kThreads, PAR_SHADE_MIN_CTAS)
 k_shade(const __grid_constant__ ShadeParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ShadeSmem& s = *reinterpret_cast<ShadeSmem*>(smem_raw);
@@ -159,11 +171,23 @@ k_shade(const __grid_constant__ ShadeParams p) {
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
     const int n_lights = p.n_lights;
 
+    // Optional barrier-to-barrier phase timing (debug; p.phase_cycles is NULL in production).
+    enum { kPhLoad, kPhFind, kPhCompact, kPhSetup, kPhWalk, kPhCounts, kPhDecide, kPhGather, kPhShade, kPhTail };
+    long long t_mark = 0;
+    if (p.phase_cycles && tid == 0) t_mark = clock64();
+    auto mark = [&](int phase) {
+        if (p.phase_cycles && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(&p.phase_cycles[phase], (unsigned long long)(now - t_mark));
+            t_mark = now;
+        }
+    };
+
     // ---- load the tile: start-bin z ("group") of every hit pixel; miss pixels are final ----
-    int gz[kTileRowsPerThread];
+    int gz[kPixPerThread];
 #pragma unroll
-    for (int m = 0; m < kTileRowsPerThread; m++) {
-        const int pidx = m * kTileThreads + tid;  // pixel (row pidx / 40, column pidx % 40) of the tile
+    for (int m = 0; m < kPixPerThread; m++) {
+        const int pidx = m * kThreads + tid;  // pixel (row pidx / 40, column pidx % 40) of the tile
         const int j = ty * kBin + pidx / kBin;
         gz[m] = kNoGroup;
         if (j >= ra && j < rb) {
@@ -183,14 +207,16 @@ k_shade(const __grid_constant__ ShadeParams p) {
         // ---- next group: the smallest start-bin z not yet processed in this tile ----
         if (tid == 0) s.group = kNoGroup;
         __syncthreads();
+        mark(last_group == -0x7fffffff - 1 ? kPhLoad : kPhShade);
         int mine = kNoGroup;
 #pragma unroll
-        for (int m = 0; m < kTileRowsPerThread; m++)
+        for (int m = 0; m < kPixPerThread; m++)
             if (gz[m] > last_group) mine = min(mine, gz[m]);
 #pragma unroll
         for (int o = 16; o; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
         if (lane == 0 && mine != kNoGroup) atomicMin(&s.group, mine);
         __syncthreads();
+        mark(kPhFind);
         const int group = s.group;
         if (group == kNoGroup) break;
         last_group = group;
@@ -198,12 +224,12 @@ k_shade(const __grid_constant__ ShadeParams p) {
         // ---- compact the group's pixels into a dense list ----
         int my_n = 0;
 #pragma unroll
-        for (int m = 0; m < kTileRowsPerThread; m++) my_n += (gz[m] == group);
+        for (int m = 0; m < kPixPerThread; m++) my_n += (gz[m] == group);
         int pos = block_exclusive_scan(my_n, s);
         const int npix = s.scan_total;
 #pragma unroll
-        for (int m = 0; m < kTileRowsPerThread; m++)
-            if (gz[m] == group) s.pix[pos++] = (unsigned short)(m * kTileThreads + tid);
+        for (int m = 0; m < kPixPerThread; m++)
+            if (gz[m] == group) s.pix[pos++] = (unsigned short)(m * kThreads + tid);
 
         // start bin of every pixel of the group (alternative.cpp:724-727, quirk Q11)
         const int start = flat_bin(d, bx, ty, group);
@@ -216,6 +242,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
         while (l_cur < n_lights) {
             // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
             __syncthreads();  // previous round fully consumed (lists, segments, pix list complete)
+            mark(fresh ? kPhCompact : kPhShade);
             if (tid < nseg_try && l_cur + tid < n_lights) {
                 const short4 lt = p.lights[l_cur + tid];
                 // light bin, alternative.cpp:729-732 ('/' truncates toward zero)
@@ -234,23 +261,30 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 g.count = 0;
                 g.fill = 0;
             }
-            for (int i = tid; i < kHashSize; i += kTileThreads) s.hash[i] = kEmpty;
+            for (int i = tid; i < kHashSize; i += kThreads) s.hash[i] = kEmpty;
             __syncthreads();
+            mark(kPhSetup);
             const int nseg = min(nseg_try, n_lights - l_cur);
             if (tid == 0) {
+                // run length: about one work item per thread, so the serial part of a walk stays short
+                int steps = 0;
+                for (int q = 0; q < nseg; q++) steps += s.seg[q].kb - s.seg[q].ka;
+                const int run = min(kMaxRun, max(1, (steps + kThreads - 1) / kThreads));
                 int items = 0;
                 for (int q = 0; q < nseg; q++) {
                     s.seg[q].item0 = items;
-                    items += (s.seg[q].kb - s.seg[q].ka + kRun - 1) / kRun;
+                    items += (s.seg[q].kb - s.seg[q].ka + run - 1) / run;
                 }
                 s.n_items = items;
+                s.run = run;
                 s.n_occ = 0;
             }
             __syncthreads();
+            mark(kPhSetup);
 
             // C. phase 1: walk.  One thread per run of kRun steps of one segment.
-            const int n_items = s.n_items;
-            for (int it = tid; it < n_items; it += kTileThreads) {
+            const int n_items = s.n_items, kRun = s.run;
+            for (int it = tid; it < n_items; it += kThreads) {
                 int q = 0;
                 while (q + 1 < nseg && s.seg[q + 1].item0 <= it) q++;
                 const Segment& g = s.seg[q];
@@ -258,13 +292,22 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 const float sx = g.sx, sy = g.sy, sz = g.sz;
                 // sequential fp32 accumulation from the start bin (quirk Q15)
                 float px = (float)bx, py = (float)ty, pz = (float)group;
-                for (int k = 0; k < k0; k++) {
+                int k = 0;
+                for (; k + 8 <= k0; k += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        px = px + sx;
+                        py = py + sy;
+                        pz = pz + sz;
+                    }
+                }
+                for (; k < k0; k++) {
                     px = px + sx;
                     py = py + sy;
                     pz = pz + sz;
                 }
                 int x0 = (int)px, y0 = (int)py, z0 = (int)pz;
-                for (int k = k0; k < k1; k++) {
+                for (k = k0; k < k1; k++) {
                     px = px + sx;
                     py = py + sy;
                     pz = pz + sz;
@@ -290,29 +333,32 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 }
             }
             __syncthreads();
+            mark(kPhWalk);
             // phase 1b: counts of the occupied bins
             const int n_occ_all = s.n_occ, n_occ = min(n_occ_all, kOccCap);
-            for (int o = tid; o < n_occ; o += kTileThreads) {
+            for (int o = tid; o < n_occ; o += kThreads) {
                 const uint2 e = s.occ[o];
                 const int c = p.cnt[e.x] & (kSlots - 1);
                 s.occ[o].y = e.y | (unsigned)c;
                 atomicAdd(&s.seg[e.y >> 8].count, c);
             }
             __syncthreads();
-            // D. how many leading segments fit the box list?
-            if (tid == 0) {
-                int fit = 0, total = 0;
-                if (n_occ_all <= kOccCap) {
-                    while (fit < nseg && total + s.seg[fit].count <= kListCap) {
-                        s.seg[fit].base = total;
-                        total += s.seg[fit].count;
-                        fit++;
-                    }
+            mark(kPhCounts);
+            // D. how many leading segments fit the box list?  (every thread, redundantly)
+            int n_fit = 0;
+            if (n_occ_all <= kOccCap) {
+                int total = 0;
+                while (n_fit < nseg && total + s.seg[n_fit].count <= kListCap) {
+                    total += s.seg[n_fit].count;
+                    n_fit++;
                 }
-                s.n_fit = fit;
             }
-            __syncthreads();
-            const int n_fit = s.n_fit;
+            if (tid < n_fit) {  // base of segment tid in the box list
+                int base = 0;
+                for (int q = 0; q < tid; q++) base += s.seg[q].count;
+                s.seg[tid].base = base;
+            }
+            mark(kPhDecide);
             if (n_fit == 0) {  // shrink: fewer lights first, then fewer steps of the first light
                 if (nseg_try > 1) {
                     nseg_try = max(1, nseg / 2);
@@ -324,13 +370,16 @@ k_shade(const __grid_constant__ ShadeParams p) {
             }
 
             // E. phase 2: gather + de-duplicate the boxes of the fitting segments
-            for (int idx = tid; idx < n_occ * kSlots; idx += kTileThreads) {
-                const uint2 e = s.occ[idx >> 3];
-                const int slot = idx & 7, c = e.y & 0xff, q = e.y >> 8;
-                if (slot >= c || q >= n_fit) continue;
+            for (int o = tid; o < n_occ; o += kThreads) {
+              const uint2 e = s.occ[o];
+              const int c = e.y & 0xff, q = e.y >> 8;
+              if (q >= n_fit) continue;
+              int base = 0;
+              for (int r = 0; r < q; r++) base += s.seg[r].count;
+              for (int slot = 0; slot < c; slot++) {
                 const int ent = p.ids[e.x * kSlots + slot];
                 const unsigned key = (unsigned)q << 26 | (unsigned)ent;
-                unsigned h = (key * 2654435761u) >> 21;
+                unsigned h = (key * 2654435761u) >> (32 - kHashBits);
                 bool fresh_key;
                 for (;;) {
                     const unsigned old = atomicCAS(&s.hash[h], kEmpty, key);
@@ -342,17 +391,19 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 }
                 if (!fresh_key) continue;
                 const Box b = unpack_box(p.boxes[ent]);
-                const int at = s.seg[q].base + atomicAdd(&s.seg[q].fill, 1);
+                const int at = base + atomicAdd(&s.seg[q].fill, 1);
                 s.list[2 * at] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(ent));
                 s.list[2 * at + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
                                                  (float)(b.pz + b.ez), 0.f);
+              }
             }
             __syncthreads();
+            mark(kPhGather);
 
             // F. phase 3: one lane per pixel of the group
             const bool final_round = s.seg[n_fit - 1].light == n_lights - 1 &&
                                      s.seg[n_fit - 1].kb == s.seg[n_fit - 1].steps;
-            for (int qb = tid - lane; qb < npix; qb += kTileThreads) {
+            for (int qb = tid - lane; qb < npix; qb += kThreads) {
                 const int qi = qb + lane;
                 const bool valid = qi < npix;
                 const int pidx = valid ? s.pix[qi] : 0;
@@ -366,7 +417,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     nx = __ldg(nrm);
                     ny = __ldg(nrm + 1);
                     nz = __ldg(nrm + 2);
-                    if (!fresh) acc = s.acc[qi];
+                    if (!fresh) acc = __uint_as_float(s.out[pidx]);
                     shadowed = s.sh[qi] != 0;  // only meaningful when segment 0 continues a light
                 }
                 // Ray origin, alternative.cpp:720-722
@@ -409,7 +460,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         // alternative.cpp:735 / 757-758
                         s.out[pidx] = quantise(c, std_min(1.f, acc + p.ambient));
                     } else {
-                        s.acc[qi] = acc;
+                        s.out[pidx] = __float_as_uint(acc);
                         s.sh[qi] = shadowed;
                     }
                 }
@@ -432,7 +483,8 @@ k_shade(const __grid_constant__ ShadeParams p) {
 
     // ---- 16-byte stores of the finished tile rows ----
     __syncthreads();
-    for (int v = tid; v < kTilePixels / 4; v += kTileThreads) {
+    mark(kPhTail);
+    for (int v = tid; v < kTilePixels / 4; v += kThreads) {
         const int j = ty * kBin + v / (kBin / 4);
         if (j < ra || j >= rb) continue;
         const uint4 px = *reinterpret_cast<const uint4*>(&s.out[4 * v]);
@@ -451,7 +503,7 @@ cudaError_t launch_shade(const ShadeParams& p, cudaStream_t st) {
     const ViewDims& d = p.d;
     int tile_rows = (d.row1 + kBin - 1) / kBin - d.row0 / kBin;
     if (tile_rows <= 0) return cudaSuccess;
-    k_shade<<<tile_rows * d.HW, kTileThreads, sizeof(ShadeSmem), st>>>(p);
+    k_shade<<<tile_rows * d.HW, kThreads, sizeof(ShadeSmem), st>>>(p);
     return cudaGetLastError();
 }
 

@@ -38,6 +38,7 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_multi_last_error", "par_sync", "par_alloc_host", "par_free_host", "par_set_atlas", "par_set_scene",
            "par_rebuild_grid", "par_render", "par_render_device", "par_device_frame",
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
+           "par_debug_phase_timing",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
            "par_light_default", "par_scene_synthetic", "par_apply_key", "par_draw_overlay"]
 
@@ -110,6 +111,7 @@ def lib():
         L.par_get_grid.argtypes = [vp, vp, vp]
         L.par_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.par_grid_volume.argtypes = [vp]
+        L.par_debug_phase_timing.argtypes = [vp, i32, vp]
         L.par_sprite_tile_floor.argtypes = [vp]
         L.par_sprite_tile_floor.restype = None
         L.par_palette_default.argtypes = [vp]
@@ -280,6 +282,14 @@ class Renderer:
         ids = np.zeros(V * 8, np.int32)
         _check(lib().par_get_grid(self._h, _p(count), _p(ids)))
         return count, ids.reshape(V, 8)
+
+    PHASES = ["load", "find", "compact", "setup", "walk", "counts", "decide", "gather", "shade", "tail"]
+
+    def phase_timing(self, enable=True):
+        """Debug: per-phase cycle totals of k_shade since the last call (dict), then (re)arm."""
+        out = np.zeros(16, np.uint64)
+        _check(lib().par_debug_phase_timing(self._h, int(enable), _p(out)))
+        return {n: int(out[i]) for i, n in enumerate(self.PHASES)}
 
     def stats(self):
         st = Stats()

@@ -24,6 +24,12 @@ def run(name, W, H, L, boxes, lights, reps=5):
             if best is None or st["ms_total"] < best["ms_total"]:
                 best = st
         best["config"] = name
+        if os.environ.get("PAR_PHASES"):
+            r.phase_timing(True)
+            r.render(lights)
+            ph = r.phase_timing(False)
+            tot = sum(ph.values()) or 1
+            best["phases_pct"] = {k: round(100.0 * v / tot, 1) for k, v in ph.items()}
         best["mrays_s_kernels"] = best["rays"] / best["ms_total"] / 1e3
         print(json.dumps(best), flush=True)
 
