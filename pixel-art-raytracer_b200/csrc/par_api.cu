@@ -66,12 +66,16 @@ static int fail(int code, const char* fmt, const char* a = "", const char* b = "
                         "%s: %s", #call, cudaGetErrorString(e_));                        \
     } while (0)
 
+constexpr int kMaxChunks = 4;  // row chunks of the pipelined readback in par_render
+
 struct par_ctx {
     par_config cfg;
     ViewDims d;
     cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev_build0 = nullptr, ev_build1 = nullptr, ev_f0 = nullptr, ev_f1 = nullptr,
-                ev_f2 = nullptr;
+    cudaStream_t copy_stream = nullptr;  // D2H of finished row chunks, overlapping the next chunk
+    cudaEvent_t ev_build0 = nullptr, ev_build1 = nullptr, ev_f0 = nullptr, ev_f2 = nullptr, ev_copy = nullptr;
+    cudaEvent_t ev_chunk[kMaxChunks][3] = {};
+    int n_chunks = 1;
     // scene
     int4* d_raw = nullptr;
     int4* d_boxes = nullptr;
@@ -82,7 +86,7 @@ struct par_ctx {
     // grid
     int* d_cnt = nullptr;
     int* d_ids = nullptr;
-    unsigned* d_occ_mask = nullptr;
+    unsigned* d_occ4 = nullptr;
     LoaderCounters* d_ctr = nullptr;
     LoaderCounters* h_ctr = nullptr;  // pinned
     // atlas
@@ -122,7 +126,7 @@ int run_loader(par_ctx* c) {
     PAR_CUDA(cudaEventRecord(c->ev_build0, c->stream));
     PAR_CUDA(launch_scene_loader(c->d_raw, c->has_sprite_ids ? c->d_sprite_ids : nullptr,
                                  c->n_entities, c->n_sprites, c->d, c->d_boxes, c->d_cnt, c->d_ids,
-                                 c->d_occ_mask, c->d_survivors, c->d_ctr, c->stream, &c->launches_build));
+                                 c->d_occ4, c->d_survivors, c->d_ctr, c->stream, &c->launches_build));
     PAR_CUDA(cudaEventRecord(c->ev_build1, c->stream));
     PAR_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(LoaderCounters), cudaMemcpyDeviceToHost,
                              c->stream));
@@ -195,13 +199,16 @@ int par_create(par_ctx** out, const par_config* cfg) {
         c->stream = c->own_stream;
         PAR_CUDA(cudaEventCreate(&c->ev_build0));
         PAR_CUDA(cudaEventCreate(&c->ev_build1));
+        PAR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         PAR_CUDA(cudaEventCreate(&c->ev_f0));
-        PAR_CUDA(cudaEventCreate(&c->ev_f1));
         PAR_CUDA(cudaEventCreate(&c->ev_f2));
+        PAR_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+        for (auto& ev : c->ev_chunk)
+            for (cudaEvent_t& e : ev) PAR_CUDA(cudaEventCreate(&e));
         size_t px = (size_t)d.W * d.H;
         PAR_CUDA(cudaMalloc(&c->d_cnt, sizeof(int) * (size_t)d.V));
         PAR_CUDA(cudaMalloc(&c->d_ids, sizeof(int) * (size_t)d.V * kSlots));
-        PAR_CUDA(cudaMalloc(&c->d_occ_mask, sizeof(unsigned) * (((size_t)d.V + 31) / 32)));
+        PAR_CUDA(cudaMalloc(&c->d_occ4, sizeof(unsigned) * (((size_t)d.V + 7) / 8)));
         PAR_CUDA(cudaMalloc(&c->d_ctr, sizeof(LoaderCounters)));
         PAR_CUDA(cudaMallocHost(&c->h_ctr, sizeof(LoaderCounters)));
         memset(c->h_ctr, 0, sizeof(LoaderCounters));
@@ -231,7 +238,7 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_survivors);
     cudaFree(c->d_cnt);
     cudaFree(c->d_ids);
-    cudaFree(c->d_occ_mask);
+    cudaFree(c->d_occ4);
     cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     cudaFree(c->d_atlas_depth);
@@ -243,9 +250,13 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_expanded);
     cudaFree(c->d_texel);
     cudaFree(c->d_phase_cycles);
-    cudaEvent_t evs[] = {c->ev_build0, c->ev_build1, c->ev_f0, c->ev_f1, c->ev_f2};
+    cudaEvent_t evs[] = {c->ev_build0, c->ev_build1, c->ev_f0, c->ev_f2, c->ev_copy};
     for (cudaEvent_t e : evs)
         if (e) cudaEventDestroy(e);
+    for (auto& ev : c->ev_chunk)
+        for (cudaEvent_t e : ev)
+            if (e) cudaEventDestroy(e);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
 }
@@ -387,11 +398,15 @@ int par_rebuild_grid(par_ctx* c) {
     return run_loader(c);
 }
 
-int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d_rgba) {
+// Launch primary + shade for the context's band into d_out.  With host_out the band is cut
+// into up to kMaxChunks row chunks (whole tile rows) and the D2H copy of chunk k overlaps the
+// rendering of chunk k+1 on a second stream — at 4K the 33 MB readback takes about as long as
+// the kernels, so the drop-in call is roughly max(render, copy) instead of their sum.
+static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4* d_out, par_color* host_out) {
     if (!c || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
-        return fail(PAR_ERR_INVALID_ARG, "par_render_device: bad argument (at most 64 lights)%s%s");
+        return fail(PAR_ERR_INVALID_ARG, "par_render: bad argument (at most 64 lights)%s%s");
     if (!c->scene_set || c->n_sprites == 0)
-        return fail(PAR_ERR_STATE, "par_render_device: set the atlas and the scene first%s%s");
+        return fail(PAR_ERR_STATE, "par_render: set the atlas and the scene first%s%s");
     DeviceGuard guard(c->cfg.device);
     const ViewDims& d = c->d;
     PrimaryParams pp;
@@ -402,35 +417,63 @@ int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d
     pp.atlas_depth = c->d_atlas_depth;
     pp.n_sprites = c->n_sprites;
     pp.gbuf = c->d_gbuf;
-    pp.tile_row_first = d.row0 / kBin;
     ShadeParams sp;
     sp.d = d;
     sp.cnt = c->d_cnt;
     sp.ids = c->d_ids;
-    sp.occ_mask = c->d_occ_mask;
+    sp.occ4 = c->d_occ4;
     sp.boxes = c->d_boxes;
     sp.gbuf = c->d_gbuf;
     sp.atlas_normal = c->d_atlas_normal;
     sp.atlas_color = c->d_atlas_color;
     sp.palette = c->d_palette;
-    sp.out = d_rgba ? static_cast<uchar4*>(d_rgba) : c->d_frame;
+    sp.out = d_out;
     sp.n_lights = n_lights;
     sp.ambient = c->ambient;
-    sp.tile_row_first = d.row0 / kBin;
     sp.phase_cycles = c->d_phase_cycles;  // NULL unless par_debug_phase_timing enabled it
     memset(sp.lights, 0, sizeof sp.lights);
     for (int l = 0; l < n_lights; l++)
         sp.lights[l] = make_short4(lights[l].x, lights[l].y, lights[l].z, lights[l].radius);
+
+    const int tile0 = d.row0 / kBin, tile1 = (d.row1 + kBin - 1) / kBin;
+    int n_chunks = 1;
+    if (host_out && tile1 - tile0 >= 4 * kMaxChunks) n_chunks = kMaxChunks;  // >= 640 rows
     PAR_CUDA(cudaEventRecord(c->ev_f0, c->stream));
-    PAR_CUDA(launch_primary(pp, c->stream));
-    PAR_CUDA(cudaEventRecord(c->ev_f1, c->stream));
-    PAR_CUDA(launch_shade(sp, c->stream));
+    for (int k = 0; k < n_chunks; k++) {
+        const int ta = tile0 + (tile1 - tile0) * k / n_chunks, tb = tile0 + (tile1 - tile0) * (k + 1) / n_chunks;
+        const int ra = ta * kBin > d.row0 ? ta * kBin : d.row0, rb = tb * kBin < d.row1 ? tb * kBin : d.row1;
+        pp.d.row0 = sp.d.row0 = ra;
+        pp.d.row1 = sp.d.row1 = rb;
+        pp.tile_row_first = sp.tile_row_first = ta;
+        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][0], c->stream));
+        PAR_CUDA(launch_primary(pp, c->stream));
+        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][1], c->stream));
+        PAR_CUDA(launch_shade(sp, c->stream));
+        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][2], c->stream));
+        if (host_out) {
+            const size_t first = (size_t)ra * d.W, count = (size_t)(rb - ra) * d.W;
+            cudaStream_t cs = n_chunks > 1 ? c->copy_stream : c->stream;
+            if (n_chunks > 1) PAR_CUDA(cudaStreamWaitEvent(cs, c->ev_chunk[k][2], 0));
+            PAR_CUDA(cudaMemcpyAsync(host_out + first, d_out + first, sizeof(par_color) * count,
+                                     cudaMemcpyDeviceToHost, cs));
+        }
+    }
     PAR_CUDA(cudaEventRecord(c->ev_f2, c->stream));
-    c->launches_frame = 2;
+    if (host_out && n_chunks > 1) {  // make the context's stream cover the copies too
+        PAR_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
+        PAR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
+    }
+    c->n_chunks = n_chunks;
+    c->launches_frame = 2 * n_chunks;
     c->last_n_lights = n_lights;
     c->frame_valid = true;
     c->frame_timed = true;
     return PAR_OK;
+}
+
+int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d_rgba) {
+    return render_impl(c, lights, n_lights, d_rgba ? static_cast<uchar4*>(d_rgba) : (c ? c->d_frame : nullptr),
+                       nullptr);
 }
 
 void* par_device_frame(par_ctx* c) { return c ? c->d_frame : nullptr; }
@@ -461,8 +504,13 @@ int par_get_stats(par_ctx* c, par_stats* st) {
     memset(st, 0, sizeof *st);
     if (c->build_timed) PAR_CUDA(cudaEventElapsedTime(&st->ms_grid_build, c->ev_build0, c->ev_build1));
     if (c->frame_timed) {
-        PAR_CUDA(cudaEventElapsedTime(&st->ms_primary, c->ev_f0, c->ev_f1));
-        PAR_CUDA(cudaEventElapsedTime(&st->ms_shade, c->ev_f1, c->ev_f2));
+        for (int k = 0; k < c->n_chunks; k++) {
+            float a = 0.f, b = 0.f;
+            PAR_CUDA(cudaEventElapsedTime(&a, c->ev_chunk[k][0], c->ev_chunk[k][1]));
+            PAR_CUDA(cudaEventElapsedTime(&b, c->ev_chunk[k][1], c->ev_chunk[k][2]));
+            st->ms_primary += a;
+            st->ms_shade += b;
+        }
         PAR_CUDA(cudaEventElapsedTime(&st->ms_total, c->ev_f0, c->ev_f2));
     }
     st->kernel_launches = c->launches_build + c->launches_frame;
@@ -476,13 +524,9 @@ int par_get_stats(par_ctx* c, par_stats* st) {
 int par_render(par_ctx* c, const par_light* lights, int n_lights, par_color* out_rgba,
                par_pixel* out_gbuf, par_stats* stats) {
     if (!c || !out_rgba) return fail(PAR_ERR_INVALID_ARG, "par_render: null argument%s%s");
-    int rc = par_render_device(c, lights, n_lights, nullptr);
+    int rc = render_impl(c, lights, n_lights, c->d_frame, out_rgba);
     if (rc != PAR_OK) return rc;
     DeviceGuard guard(c->cfg.device);
-    const ViewDims& d = c->d;
-    size_t first = (size_t)d.row0 * d.W, count = (size_t)(d.row1 - d.row0) * d.W;
-    PAR_CUDA(cudaMemcpyAsync(out_rgba + first, c->d_frame + first, sizeof(par_color) * count,
-                             cudaMemcpyDeviceToHost, c->stream));
     if (out_gbuf && (rc = expand_gbuffer(c, out_gbuf, nullptr)) != PAR_OK) return rc;
     PAR_CUDA(cudaStreamSynchronize(c->stream));
     if ((rc = check_scene_flag(c)) != PAR_OK) return rc;

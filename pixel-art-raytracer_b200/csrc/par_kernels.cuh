@@ -14,7 +14,7 @@ struct LoaderCounters {
 };
 cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,
                                 const ViewDims& d, int4* boxes, int* cnt, int* ids,
-                                unsigned* occ_mask, int* survivors, LoaderCounters* ctr,
+                                unsigned* occ4, int* survivors, LoaderCounters* ctr,
                                 cudaStream_t s, int* launches);
 
 // ---- primary rays (alternative.cpp:271-383) ----
@@ -38,7 +38,7 @@ struct ShadeParams {
     ViewDims d;
     const int* cnt;
     const int* ids;
-    const unsigned* occ_mask;  // 1 bit per bin: (cnt & 7) != 0
+    const unsigned* occ4;      // 4 bits per bin: cnt & 7 (8 bins per word)
     const int4* boxes;
     const int4* gbuf;
     const float* atlas_normal;         // [n_sprites][800][3]

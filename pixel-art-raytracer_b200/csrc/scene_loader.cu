@@ -11,8 +11,9 @@
 //   2. k_select_round<r>   r = 0..6: every surviving (entity, bin) pair whose bin keeps more
 //                          than r entries proposes itself with atomicMax if it is smaller than
 //                          the bin's round r-1 winner — after round r, ids[bin*8+r] is the
-//                          (r+1)-th highest inserting entity index.  Round 0 also sets the
-//                          bin's bit in a 1-bit-per-bin occupancy mask (read by the walk).
+//                          (r+1)-th highest inserting entity index.  Round 0 also writes the
+//                          bin's wrapped count into a 4-bit-per-bin table (read by the walk:
+//                          one small load answers "occupied?" and "how many?").
 // Readers map the reference's slot s to ids[bin*8 + (cnt&7) - 1 - s].
 #include "par_kernels.cuh"
 
@@ -52,7 +53,7 @@ k_load_cull_count(const int4* __restrict__ raw, const int* __restrict__ sprite_i
 
 __global__ void __launch_bounds__(256)
 k_select_round(int round, const int* __restrict__ survivors, const int4* __restrict__ boxes,
-               ViewDims d, const int* __restrict__ cnt, int* ids, unsigned* __restrict__ occ_mask,
+               ViewDims d, const int* __restrict__ cnt, int* ids, unsigned* __restrict__ occ4,
                const LoaderCounters* __restrict__ ctr) {
     if (round >= ctr->max_inserts_per_bin) return;  // no bin keeps more than `round` entries
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +68,7 @@ k_select_round(int round, const int* __restrict__ survivors, const int4* __restr
                 int f = flat_bin(d, x, y, z);
                 int keep = cnt[f] & (kSlots - 1);
                 if (round >= keep) continue;
-                if (round == 0) atomicOr(&occ_mask[f >> 5], 1u << (f & 31));  // bin reads non-empty
+                if (round == 0) atomicOr(&occ4[f >> 3], (unsigned)keep << ((f & 7) * 4));  // idempotent: same value from every inserter
                 int prev = round ? ids[f * kSlots + round - 1] : 0x7fffffff;
                 if (e < prev) atomicMax(&ids[f * kSlots + round], e);
             }
@@ -76,12 +77,12 @@ k_select_round(int round, const int* __restrict__ survivors, const int4* __restr
 // Host-side launcher (called from par_api.cu).
 cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,
                                 const ViewDims& d, int4* boxes, int* cnt, int* ids,
-                                unsigned* occ_mask, int* survivors, LoaderCounters* ctr,
+                                unsigned* occ4, int* survivors, LoaderCounters* ctr,
                                 cudaStream_t s, int* launches) {
     cudaError_t err;
     if ((err = cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)d.V, s))) return err;
     if ((err = cudaMemsetAsync(ids, 0xff, sizeof(int) * (size_t)d.V * kSlots, s))) return err;
-    if ((err = cudaMemsetAsync(occ_mask, 0, sizeof(unsigned) * (((size_t)d.V + 31) / 32), s))) return err;
+    if ((err = cudaMemsetAsync(occ4, 0, sizeof(unsigned) * (((size_t)d.V + 7) / 8), s))) return err;
     if ((err = cudaMemsetAsync(ctr, 0, sizeof(LoaderCounters), s))) return err;
     if (n > 0) {
         int blocks = (n + 255) / 256;
@@ -90,7 +91,7 @@ cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, i
         // The survivor count lives on the device; size the round grids for the worst case
         // (every entity survives) and let surplus threads exit on the device-side count.
         for (int r = 0; r < kSlots - 1; r++)
-            k_select_round<<<blocks, 256, 0, s>>>(r, survivors, boxes, d, cnt, ids, occ_mask, ctr);
+            k_select_round<<<blocks, 256, 0, s>>>(r, survivors, boxes, d, cnt, ids, occ4, ctr);
         *launches += kSlots;
     }
     return cudaGetLastError();

@@ -47,7 +47,8 @@ constexpr int kHashSize = 2 * kListCap;       // de-duplication set
 constexpr int kHashBits = kListCap == 1024 ? 11 : kListCap == 512 ? 10 : 9;
 constexpr int kOccCap = kListCap;             // occupied probed bins per round
 constexpr int kSegMax = 16;                   // (light, step range) segments per round
-constexpr int kMaxRun = 16;                   // most walk steps per phase-1 thread
+constexpr int kMaxRun = 32;                   // most walk steps per phase-1 thread
+constexpr int kScratchRows = kListCap * 8 / kThreads;  // ints per thread in the idle box list
 constexpr int kTilePixels = kBin * kBin;
 constexpr int kPixPerThread = kTilePixels / kThreads;
 constexpr int kNoGroup = 0x7fffffff;
@@ -113,14 +114,34 @@ __device__ __forceinline__ bool slab_hit_fast(const float4 lo, const float4 hi, 
     return tmax >= tmin;
 }
 
-template <bool kExact>
+// Same test again when, in addition, the signs of the three inverse-direction components are
+// known (octant bit a set = component a negative).  With lo <= hi, subtraction and a
+// multiplication by a constant are monotonic in fp32, so min(x1,x2) IS the product of the
+// near corner (lo for a positive component, hi for a negative one) and max(x1,x2) that of
+// the far corner: the six inner min/max disappear.
+template <int kOctant>
+__device__ __forceinline__ bool slab_hit_octant(const float4 lo, const float4 hi, float ox, float oy,
+                                                float oz, float ix, float iy, float iz) {
+    const float nx = ((kOctant & 1) ? hi.x : lo.x) - ox, fx = ((kOctant & 1) ? lo.x : hi.x) - ox;
+    const float ny = ((kOctant & 2) ? hi.y : lo.y) - oy, fy = ((kOctant & 2) ? lo.y : hi.y) - oy;
+    const float nz = ((kOctant & 4) ? hi.z : lo.z) - oz, fz = ((kOctant & 4) ? lo.z : hi.z) - oz;
+    const float tmin = fmaxf(fmaxf(nx * ix, ny * iy), nz * iz);
+    const float tmax = fminf(fminf(fx * ix, fy * iy), fz * iz);
+    return tmax >= tmin;
+}
+
+// kMode 0..7: sign octant known for the whole warp; 8: NaN-free, mixed signs; 9: exact.
+template <int kMode>
 __device__ __forceinline__ bool any_box_hit(const float4* __restrict__ boxes, int n, int self,
                                             float ox, float oy, float oz, float ix, float iy,
                                             float iz) {
+#pragma unroll 2
     for (int e = 0; e < n; e++) {
         const float4 lo = boxes[2 * e], hi = boxes[2 * e + 1];
-        const bool hit = kExact ? slab_hit_exact(lo, hi, ox, oy, oz, ix, iy, iz)
-                                : slab_hit_fast(lo, hi, ox, oy, oz, ix, iy, iz);
+        bool hit;
+        if (kMode == 9) hit = slab_hit_exact(lo, hi, ox, oy, oz, ix, iy, iz);
+        else if (kMode == 8) hit = slab_hit_fast(lo, hi, ox, oy, oz, ix, iy, iz);
+        else hit = slab_hit_octant<kMode & 7>(lo, hi, ox, oy, oz, ix, iy, iz);
         if (hit && __float_as_int(lo.w) != self) return true;  // quirk Q17: own entity never shadows
     }
     return false;
@@ -173,6 +194,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
 
     // Optional barrier-to-barrier phase timing (debug; p.phase_cycles is NULL in production).
     enum { kPhLoad, kPhFind, kPhCompact, kPhSetup, kPhWalk, kPhCounts, kPhDecide, kPhGather, kPhShade, kPhTail };
+    static_assert(kScratchRows >= 14, "scratch too small for two walk steps");
     long long t_mark = 0;
     if (p.phase_cycles && tid == 0) t_mark = clock64();
     auto mark = [&](int phase) {
@@ -191,7 +213,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
         const int j = ty * kBin + pidx / kBin;
         gz[m] = kNoGroup;
         if (j >= ra && j < rb) {
-            const int4 g = p.gbuf[(size_t)j * d.W + bx * kBin + pidx % kBin];
+            const int4 g = __ldcs(&p.gbuf[(size_t)j * d.W + bx * kBin + pidx % kBin]);  // streamed: keep L1 for the grid
             if (g.w >= 0 && n_lights > 0) {
                 gz[m] = g.z / kBin;  // ray_bin_z, alternative.cpp:727
             } else {
@@ -282,8 +304,12 @@ k_shade(const __grid_constant__ ShadeParams p) {
             __syncthreads();
             mark(kPhSetup);
 
-            // C. phase 1: walk.  One thread per run of kRun steps of one segment.
+            // C. phase 1: walk.  One thread per run of kRun steps of one segment.  The run is
+            // processed in sub-chunks: first the distinct probed bins of up to 8 steps are
+            // listed (ALU only) in a thread-private column of shared scratch, then their 4-bit
+            // counts are fetched as one batch of independent loads.
             const int n_items = s.n_items, kRun = s.run;
+            int* scratch = reinterpret_cast<int*>(s.list);  // [kScratchRows][kThreads]; the box list is idle now
             for (int it = tid; it < n_items; it += kThreads) {
                 int q = 0;
                 while (q + 1 < nseg && s.seg[q + 1].item0 <= it) q++;
@@ -307,43 +333,60 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     pz = pz + sz;
                 }
                 int x0 = (int)px, y0 = (int)py, z0 = (int)pz;
-                for (k = k0; k < k1; k++) {
-                    px = px + sx;
-                    py = py + sy;
-                    pz = pz + sz;
-                    const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
-                    const int cx = x1 != x0, cy = y1 != y0, cz = z1 != z0;
-                    // The 7 probes of a step are the bins {x0|x1} x {y0|y1} x {z0|z1} minus "all
-                    // old"; the all-old bin was the previous step's last probe (or the start
-                    // bin, which is skipped anyway: quirk Q16).
+                while (k < k1) {
+                    int n = 0;
+                    for (int u = 0; u < 8 && k < k1 && n + 7 <= kScratchRows; u++, k++) {
+                        px = px + sx;
+                        py = py + sy;
+                        pz = pz + sz;
+                        const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
+                        const int cx = x1 != x0, cy = y1 != y0, cz = z1 != z0;
+                        // The 7 probes of a step are the bins {x0|x1} x {y0|y1} x {z0|z1} minus
+                        // "all old"; the all-old bin was the previous step's last probe (or the
+                        // start bin, which is skipped anyway: quirk Q16).
 #pragma unroll
-                    for (int mask = 1; mask < 8; mask++) {
-                        if (((mask & 1) && !cx) || ((mask & 2) && !cy) || ((mask & 4) && !cz))
-                            continue;  // same bin as the probe with that bit cleared
-                        const int f = flat_bin(d, (mask & 1) ? x1 : x0, (mask & 2) ? y1 : y0,
-                                               (mask & 4) ? z1 : z0);
-                        if (f == start || f < 0 || f >= d.V) continue;  // Q16 / Q18
-                        if (!(__ldg(&p.occ_mask[f >> 5]) >> (f & 31) & 1)) continue;  // empty bin
-                        const int o = atomicAdd(&s.n_occ, 1);
-                        if (o < kOccCap) s.occ[o] = make_uint2((unsigned)f, (unsigned)q << 8);
+                        for (int mask = 1; mask < 8; mask++) {
+                            if (((mask & 1) && !cx) || ((mask & 2) && !cy) || ((mask & 4) && !cz))
+                                continue;  // same bin as the probe with that bit cleared
+                            const int f = flat_bin(d, (mask & 1) ? x1 : x0, (mask & 2) ? y1 : y0,
+                                                   (mask & 4) ? z1 : z0);
+                            if (f == start || f < 0 || f >= d.V) continue;  // Q16 / Q18
+                            scratch[n * kThreads + tid] = f;
+                            n++;
+                        }
+                        x0 = x1;
+                        y0 = y1;
+                        z0 = z1;
                     }
-                    x0 = x1;
-                    y0 = y1;
-                    z0 = z1;
+                    int found = 0, boxes = 0;
+                    for (int i = 0; i < n; i += 4) {
+                        int f[4], c[4];
+#pragma unroll
+                        for (int u = 0; u < 4; u++) f[u] = i + u < n ? scratch[(i + u) * kThreads + tid] : -1;
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            c[u] = f[u] >= 0 ? (__ldg(&p.occ4[f[u] >> 3]) >> ((f[u] & 7) * 4)) & 7 : 0;
+#pragma unroll
+                        for (int u = 0; u < 4; u++)
+                            if (c[u]) {  // in-place compaction: found <= i + u
+                                scratch[found * kThreads + tid] = f[u] << 3 | c[u];
+                                found++;
+                                boxes += c[u];
+                            }
+                    }
+                    if (found) {
+                        const int o = atomicAdd(&s.n_occ, found);
+                        atomicAdd(&s.seg[q].count, boxes);
+                        for (int j = 0; j < found; j++) {
+                            const int e = scratch[j * kThreads + tid];
+                            if (o + j < kOccCap) s.occ[o + j] = make_uint2((unsigned)(e >> 3), (unsigned)q << 8 | (e & 7));
+                        }
+                    }
                 }
             }
             __syncthreads();
             mark(kPhWalk);
-            // phase 1b: counts of the occupied bins
             const int n_occ_all = s.n_occ, n_occ = min(n_occ_all, kOccCap);
-            for (int o = tid; o < n_occ; o += kThreads) {
-                const uint2 e = s.occ[o];
-                const int c = p.cnt[e.x] & (kSlots - 1);
-                s.occ[o].y = e.y | (unsigned)c;
-                atomicAdd(&s.seg[e.y >> 8].count, c);
-            }
-            __syncthreads();
-            mark(kPhCounts);
             // D. how many leading segments fit the box list?  (every thread, redundantly)
             int n_fit = 0;
             if (n_occ_all <= kOccCap) {
@@ -412,7 +455,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 float nx = 0.f, ny = 0.f, nz = 0.f, acc = 0.f;
                 bool shadowed = false;
                 if (valid) {
-                    g = p.gbuf[(size_t)j * d.W + i];
+                    g = __ldcs(&p.gbuf[(size_t)j * d.W + i]);
                     const float* nrm = p.atlas_normal + ((g.w >> 10) * kTexels + (g.w & 1023)) * 3;
                     nx = __ldg(nrm);
                     ny = __ldg(nrm + 1);
@@ -447,10 +490,30 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     // a NaN can only arise from a zero (or NaN) direction component (quirk Q13)
                     const bool nan_free = fabsf(tx) > 0.f && fabsf(tyv) > 0.f && fabsf(tz) > 0.f;
                     const float4* boxes = s.list + 2 * sg.base;
-                    if (__any_sync(0xffffffffu, test && !nan_free)) {
-                        if (test && any_box_hit<true>(boxes, n, g.x, ox, oy, oz, ix, iy, iz)) shadowed = true;
-                    } else {
-                        if (test && any_box_hit<false>(boxes, n, g.x, ox, oy, oz, ix, iy, iz)) shadowed = true;
+                    const unsigned testing = __ballot_sync(0xffffffffu, test);
+                    if (testing) {
+                        // warp-uniform choice of the slab-test variant
+                        const int octant = (ix < 0.f) | (iy < 0.f) << 1 | (iz < 0.f) << 2;
+                        const int first = __shfl_sync(0xffffffffu, octant, __ffs(testing) - 1);
+                        int mode = first;
+                        if (__any_sync(0xffffffffu, test && octant != first)) mode = 8;
+                        if (__any_sync(0xffffffffu, test && !nan_free)) mode = 9;
+                        bool hit = false;
+                        if (test) {
+                            switch (mode) {
+                                case 0: hit = any_box_hit<0>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 1: hit = any_box_hit<1>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 2: hit = any_box_hit<2>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 3: hit = any_box_hit<3>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 4: hit = any_box_hit<4>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 5: hit = any_box_hit<5>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 6: hit = any_box_hit<6>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 7: hit = any_box_hit<7>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                case 8: hit = any_box_hit<8>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                                default: hit = any_box_hit<9>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
+                            }
+                        }
+                        if (hit) shadowed = true;
                     }
                     if (sg.kb == sg.steps && lit_candidate && !shadowed) acc = acc + lam;
                 }

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--outer", action="store_true", help="attribute inlined code to its call site")
     ap.add_argument("--sass", action="store_true", help="list the hottest SASS instructions too")
+    ap.add_argument("--by", default="samples", choices=["samples", "inst"], help="sort key")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv"], check=True,
                          capture_output=True, text=True).stdout
@@ -89,7 +90,7 @@ def main():
     tt = sum(e[1] for e in per_line.values())
     print(f"warp instructions {ti:,}  thread instructions {tt:,}  (avg {tt / ti:.1f} active lanes)  samples {ts:,}")
     src_cache = {}
-    for key, e in sorted(per_line.items(), key=lambda kv: -kv[1][2])[:a.top]:
+    for key, e in sorted(per_line.items(), key=lambda kv: -kv[1][2 if a.by == 'samples' else 0])[:a.top]:
         f, ln = key
         if f not in src_cache:
             p = next((os.path.join(dp, f) for dp, _, fs in os.walk(ROOT) if f in fs and "build" not in dp), None)
