@@ -195,36 +195,41 @@ def ours(args):
         dist.init_process_group("nccl", device_id=dev)
     W, H, L, desc, boxes, lights = make_workload(par, args.workload)
     n_lights = len(lights)
-    from par_b200.bands import band_rows, gather_bands
-    row0, row1 = band_rows(H, world, rank)  # H/N is integral for every config
+    from par_b200.bands import gather_stripes, owned_rows
+    # interleaved 40-row stripes: tile row t belongs to rank t % N (balances the walk cost)
+    my_rows = sum(b - a for a, b in owned_rows(H, world, rank))
     rays_frame = W * H * (1 + n_lights)
 
     stream = torch.cuda.Stream(device=dev)
-    ren = par.Renderer(W, H, L, device=local, row_begin=row0, row_end=row1)
+    ren = par.Renderer(W, H, L, device=local, stripe_count=world, stripe_index=rank)
     ren.set_stream(stream.cuda_stream)
     ren.set_atlas()
-    frame = torch.zeros(H * W * 4, dtype=torch.uint8, device=dev)  # the full frame in HBM
+    frame = torch.zeros(H * W * 4, dtype=torch.uint8, device=dev)  # the full raster frame in HBM
+    staging = torch.zeros(ren.staging_bytes(), dtype=torch.uint8, device=dev) if world > 1 else None
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     h_boxes = par.pinned_empty(len(boxes), par.AABB)
     h_boxes[:] = boxes
     h_frame = par.pinned_empty((H, W), par.COLOR) if rank == 0 else None
     t_hframe = torch.from_numpy(h_frame.view(np.uint8).reshape(-1)) if rank == 0 else None
 
-    def gather():
-        gather_bands(frame, W, H, world, rank)  # in place: band r lives at offset r of frame
+    def render_and_gather():
+        if world == 1:
+            ren.render_device(lights, frame.data_ptr())
+            return
+        ren.render_device_striped(lights, staging.data_ptr())  # my stripes, contiguous in staging
+        gather_stripes(staging, world, rank)                    # in-place NCCL all-gather over NVLink
+        ren.unstripe_device(staging.data_ptr(), frame.data_ptr())  # staging -> raster frame
 
     def step_resident():
         ren.rebuild_grid()                       # device scene loader on the resident scene
-        ren.render_device(lights, frame.data_ptr())
-        gather()
+        render_and_gather()
 
     def step_e2e():
         ren.set_scene(h_boxes)                   # H2D from pinned memory + scene loader
         if world == 1:
             ren.render(lights, out=h_frame)      # the drop-in call: render + D2H into a host frame
             return
-        ren.render_device(lights, frame.data_ptr())
-        gather()
+        render_and_gather()
         if rank == 0:
             t_hframe.copy_(frame, non_blocking=True)  # D2H of the gathered frame
 
@@ -293,7 +298,7 @@ def ours(args):
     peak_ops = prop.multi_processor_count * 128 * sm_max * 1e6 / 1e12  # T lane-ops/s
     ops = (ops_tab.get(args.workload) or {}).get("algorithmic_ops")
     shade = sum(shade_ms) / len(shade_ms)
-    frac_rows = (row1 - row0) / H
+    frac_rows = my_rows / H
     # shade kernel's share of the algorithmic ops: everything but the primary-ray counters
     roofline = {"bound": "fp32_alu", "kernel": "k_shade", "unit": "Tlane-op/s", "peak": round(peak_ops, 2),
                 "peak_source": f"{prop.multi_processor_count} SMs x 128 lanes x {sm_max:.0f} MHz (1 op/lane/clk; no FMA "
@@ -310,7 +315,7 @@ def ours(args):
                                  "/ CUDA-event time of k_shade; >1 means the kernel legally skips work the reference "
                                  "does (shared grid walks, de-duplicated probes, Q19); see profiles/ for ncu pipe "
                                  "utilisation"})
-    hbm_bytes = 16.0 * W * (row1 - row0) + 4.0 * W * (row1 - row0)
+    hbm_bytes = 16.0 * W * my_rows + 4.0 * W * my_rows
     roofline["hbm"] = {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": round(hbm_bytes / (shade * 1e-3) / 1e9, 1),
                        "peak_gbs": peaks.get("hbm_gbs"), "note": "G-buffer read + RGBA8 write; not the bound"}
 
@@ -321,12 +326,13 @@ def ours(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "view": [W, H, L], "n_entities": int(len(boxes)),
                    "n_lights": int(n_lights), "rays_per_frame": rays_frame,
-                   "parallelism": f"row bands x{world}" + (" + NCCL all-gather of the RGBA8 frame" if world > 1 else ""),
+                   "parallelism": (f"interleaved 40-row stripes x{world} + in-place NCCL all-gather of the RGBA8 frame"
+                                   if world > 1 else "1 GPU"),
                    "l2": "flushed between timed steps (256 MB fill)", "frames_per_s": round(1e3 * args.steps / ms, 2)},
         "e2e": {"value": round(e2e, 1), "unit": "Mrays/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "frames_per_s": round(1e3 * args.steps / ms_e2e, 2),
                 "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4)},
-        "gpu_launches": (10 * args.steps) * world,
+        "gpu_launches": ((10 if world == 1 else 11) * args.steps) * world,
         "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
                        "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},
         "roofline": roofline, "clocks": clocks,

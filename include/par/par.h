@@ -87,7 +87,10 @@ typedef struct par_config {
     int32_t row_begin; /* this context renders rows [row_begin,row_end); */
     int32_t row_end;   /* both 0 = the whole frame (row-band multi-GPU)  */
     float ambient;     /* ambient_light, alternative.cpp:702; 0 selects 0.25f */
-    int32_t reserved[5];
+    int32_t stripe_count; /* > 1: of the band, render only the 40-row tile rows t with          */
+    int32_t stripe_index; /* t % stripe_count == stripe_index (interleaved stripes balance the   */
+                          /* per-row cost over GPUs far better than contiguous bands); 0/1 = all */
+    int32_t reserved[3];
 } par_config;
 
 /* Filled by par_render / par_get_stats; GPU times are CUDA-event milliseconds on the
@@ -154,6 +157,15 @@ int par_render(par_ctx* ctx, const par_light* lights, int n_lights, par_color* o
  * context's own frame buffer.  Use par_sync / stream ordering before consuming it. */
 int par_render_device(par_ctx* ctx, const par_light* lights, int n_lights, void* d_rgba);
 
+/* Striped multi-GPU rendering: like par_render_device, but the context's stripes are written
+ * STRIPE-MAJOR into d_staging (par_staging_bytes() bytes, laid out [stripe_count][T][40 rows][W]
+ * with T = ceil(H/40 / stripe_count)), i.e. every rank's output is one contiguous block at
+ * offset stripe_index * T * 40 * W * 4 — exactly what an in-place all-gather wants.
+ * par_unstripe_device then turns a gathered staging frame into the raster W*H frame. */
+int par_render_device_striped(par_ctx* ctx, const par_light* lights, int n_lights, void* d_staging);
+size_t par_staging_bytes(const par_ctx* ctx);
+int par_unstripe_device(par_ctx* ctx, const void* d_staging, void* d_rgba);
+
 /* Device pointer of the context's own W*H*4 frame buffer. */
 void* par_device_frame(par_ctx* ctx);
 
@@ -169,18 +181,20 @@ int par_grid_volume(const par_ctx* ctx);
  * summed over CTAs).  enable != 0 switches the instrumentation on and zeroes it. */
 int par_debug_phase_timing(par_ctx* ctx, int enable, uint64_t* out16);
 
-/* -- single-process multi-GPU: row bands + in-place ncclAllGather of the frame over NVLink -- */
-/* One par_ctx per device renders rows [i*H/n, (i+1)*H/n) of the same scene (the scene and grid
- * are replicated).  NCCL is loaded lazily with dlopen and only when n_devices > 1. */
+/* -- single-process multi-GPU: interleaved stripes + in-place ncclAllGather over NVLink ------ */
+/* One par_ctx per device renders the tile rows t with t % n == i of the same scene (the scene
+ * and grid are replicated) stripe-major into a staging frame; one in-place ncclAllGather and
+ * an un-stripe copy complete the raster frame on every device.  NCCL is loaded lazily with
+ * dlopen and only when n_devices > 1. */
 typedef struct par_multi par_multi;
 int par_multi_create(par_multi** out, const par_config* cfg, const int* devices, int n_devices);
 void par_multi_destroy(par_multi* m);
 int par_multi_size(const par_multi* m);
-par_ctx* par_multi_context(par_multi* m, int i); /* band i's context (G-buffer, stats, grid) */
+par_ctx* par_multi_context(par_multi* m, int i); /* device i's context (G-buffer, stats, grid) */
 int par_multi_set_atlas(par_multi* m, const par_sprite* sprites, int n_sprites,
                         const par_color* palette, int n_palette);
 int par_multi_set_scene(par_multi* m, const par_aabb* aabbs, const int32_t* sprite_ids, int n);
-/* Renders every band, gathers, and reads the finished frame back from device 0 into out_rgba
+/* Renders every stripe set, gathers, and reads the finished frame back from device 0 into out_rgba
  * (host, W*H; NULL = leave it in HBM, complete on every device).  Synchronous. */
 int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_color* out_rgba,
                      par_stats* stats);

@@ -1,7 +1,10 @@
 // multi_gpu.cu — single-process multi-GPU mode of the C ABI (par_multi_*): the image is split
-// into row bands, one par_ctx per device renders its band in place into a full-size frame in
-// its own HBM, and one in-place ncclAllGather over NVLink completes the frame on every device
-// (SURVEY.md §8e).  The scene/grid is replicated: a shadow ray may visit any bin.
+// into interleaved 40-row stripes (tile row t belongs to device t % n — the per-row cost of the
+// shadow walks varies strongly over the image, so contiguous bands scale badly), one par_ctx
+// per device renders its stripes STRIPE-MAJOR into a staging frame in its own HBM (its output
+// is one contiguous block), one in-place ncclAllGather over NVLink completes the staging frame
+// on every device and a copy kernel turns it into the raster frame.  The
+// scene/grid is replicated: a shadow ray may visit any bin.
 //
 // NCCL is loaded lazily with dlopen("libnccl.so.2") so that libpar_b200.so itself has no
 // link-time NCCL dependency and the one-GPU path never touches it.  (bench.py's torchrun mode
@@ -23,7 +26,6 @@ struct Nccl {
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
@@ -37,12 +39,11 @@ struct Nccl {
         PAR_SYM(CommInitAll);
         PAR_SYM(CommDestroy);
         PAR_SYM(AllGather);
-        PAR_SYM(Broadcast);
         PAR_SYM(GroupStart);
         PAR_SYM(GroupEnd);
         PAR_SYM(GetErrorString);
 #undef PAR_SYM
-        return CommInitAll && CommDestroy && AllGather && Broadcast && GroupStart && GroupEnd && GetErrorString;
+        return CommInitAll && CommDestroy && AllGather && GroupStart && GroupEnd && GetErrorString;
     }
 };
 
@@ -56,7 +57,7 @@ struct par_multi {
     int W = 0, H = 0;
     par_ctx* ctx[8] = {};
     int device[8] = {};
-    int row0[8] = {}, row1[8] = {};
+    void* staging[8] = {};  // stripe-major frames, one per device
     ncclComm_t comm[8] = {};
     bool have_comm = false;
 };
@@ -69,6 +70,13 @@ void par_multi_destroy(par_multi* m) {
     if (!m) return;
     for (int i = 0; i < m->n; i++) {
         if (m->have_comm && m->comm[i]) g_nccl.CommDestroy(m->comm[i]);
+        if (m->staging[i]) {
+            int prev = 0;
+            cudaGetDevice(&prev);
+            cudaSetDevice(m->device[i]);
+            cudaFree(m->staging[i]);
+            cudaSetDevice(prev);
+        }
         par_destroy(m->ctx[i]);
     }
     delete m;
@@ -86,17 +94,27 @@ int par_multi_create(par_multi** out, const par_config* cfg, const int* devices,
     m->n = n_devices;
     m->W = cfg->width;
     m->H = cfg->height;
-    const int rows = cfg->height / n_devices;
     for (int i = 0; i < n_devices; i++) {
         par_config c = *cfg;
         c.device = devices[i];
-        c.row_begin = i * rows;
-        c.row_end = (i == n_devices - 1) ? cfg->height : (i + 1) * rows;
+        c.row_begin = c.row_end = 0;  // whole frame, of which this context owns every n-th tile row
+        c.stripe_count = n_devices;
+        c.stripe_index = i;
         m->device[i] = devices[i];
-        m->row0[i] = c.row_begin;
-        m->row1[i] = c.row_end;
         int rc = par_create(&m->ctx[i], &c);
+        if (rc == PAR_OK && n_devices > 1) {
+            int prev = 0;
+            cudaGetDevice(&prev);
+            cudaSetDevice(devices[i]);
+            if (cudaMalloc(&m->staging[i], par_staging_bytes(m->ctx[i])) != cudaSuccess) {
+                cudaGetLastError();
+                snprintf(g_multi_err, sizeof g_multi_err, "par_multi_create: staging frame allocation failed");
+                rc = PAR_ERR_OUT_OF_MEMORY;
+            }
+            cudaSetDevice(prev);
+        }
         if (rc != PAR_OK) {
+            m->n = i + 1;
             par_multi_destroy(m);
             return rc;
         }
@@ -145,31 +163,30 @@ int par_multi_set_scene(par_multi* m, const par_aabb* aabbs, const int32_t* spri
 int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_color* out_rgba, par_stats* stats) {
     g_multi_err[0] = 0;
     if (!m) return PAR_ERR_INVALID_ARG;
-    for (int i = 0; i < m->n; i++) {
-        int rc = par_render_device(m->ctx[i], lights, n_lights, nullptr);
+    if (m->n == 1) {
+        int rc = par_render_device(m->ctx[0], lights, n_lights, nullptr);
         if (rc != PAR_OK) return rc;
-    }
-    if (m->n > 1) {
-        const size_t row_bytes = (size_t)m->W * 4;
-        const bool equal = m->H % m->n == 0;
+    } else {
+        for (int i = 0; i < m->n; i++) {  // asynchronous: all devices render their stripes concurrently
+            int rc = par_render_device_striped(m->ctx[i], lights, n_lights, m->staging[i]);
+            if (rc != PAR_OK) return rc;
+        }
+        const size_t block = par_staging_bytes(m->ctx[0]) / m->n;  // one rank's contiguous stripes
         ncclResult_t r = g_nccl.GroupStart();
-        for (int i = 0; i < m->n && r == ncclSuccess; i++) {
-            unsigned char* frame = static_cast<unsigned char*>(par_device_frame(m->ctx[i]));
-            cudaStream_t st = static_cast<cudaStream_t>(par_get_stream(m->ctx[i]));
-            if (equal) {  // in place: band i lives at offset i of every frame
-                r = g_nccl.AllGather(frame + m->row0[i] * row_bytes, frame, (m->row1[i] - m->row0[i]) * row_bytes,
-                                     ncclUint8, m->comm[i], st);
-            } else {
-                for (int b = 0; b < m->n && r == ncclSuccess; b++)
-                    r = g_nccl.Broadcast(frame + m->row0[b] * row_bytes, frame + m->row0[b] * row_bytes,
-                                         (m->row1[b] - m->row0[b]) * row_bytes, ncclUint8, b, m->comm[i], st);
-            }
+        for (int i = 0; i < m->n && r == ncclSuccess; i++) {  // in place: rank i's block sits at offset i
+            unsigned char* st = static_cast<unsigned char*>(m->staging[i]);
+            r = g_nccl.AllGather(st + i * block, st, block, ncclUint8, m->comm[i],
+                                 static_cast<cudaStream_t>(par_get_stream(m->ctx[i])));
         }
         ncclResult_t e = g_nccl.GroupEnd();
         if (r == ncclSuccess) r = e;
         if (r != ncclSuccess) {
             snprintf(g_multi_err, sizeof g_multi_err, "NCCL frame gather: %s", g_nccl.GetErrorString(r));
             return PAR_ERR_NCCL;
+        }
+        for (int i = 0; i < m->n; i++) {  // staging -> raster frame on every device
+            int rc = par_unstripe_device(m->ctx[i], m->staging[i], par_device_frame(m->ctx[i]));
+            if (rc != PAR_OK) return rc;
         }
     }
     if (out_rgba) {

@@ -47,6 +47,17 @@ k_expand_gbuf(const int4* __restrict__ gbuf, const float* __restrict__ atlas_nor
     if (out_texel) out_texel[px] = texel;
 }
 
+// Stripe-major staging frame ([n][T][40][W] uchar4) -> raster frame, 16 bytes per thread.
+__global__ void __launch_bounds__(256)
+k_unstripe(const uint4* __restrict__ staging, uint4* __restrict__ raster, int W4, int H, int n, int T) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)W4 * H) return;
+    const int j = (int)(t / W4), c = (int)(t % W4);
+    const int tile = j / kBin;
+    const int src_row = ((tile % n) * T + tile / n) * kBin + j % kBin;
+    raster[t] = staging[(size_t)src_row * W4 + c];
+}
+
 }  // namespace par
 
 using namespace par;
@@ -165,6 +176,9 @@ int par_create(par_ctx** out, const par_config* cfg) {
     if (row0 == 0 && row1 == 0) row1 = cfg->height;
     if (row0 < 0 || row1 > cfg->height || row0 >= row1)
         return fail(PAR_ERR_INVALID_ARG, "par_create: bad row band%s%s");
+    if (cfg->stripe_count < 0 || cfg->stripe_count > 64 ||
+        (cfg->stripe_count > 1 && (cfg->stripe_index < 0 || cfg->stripe_index >= cfg->stripe_count)))
+        return fail(PAR_ERR_INVALID_ARG, "par_create: bad stripe_count / stripe_index%s%s");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
         cudaGetLastError();
@@ -192,6 +206,8 @@ int par_create(par_ctx** out, const par_config* cfg) {
     d.V = d.HW * d.HH * d.HL;
     d.row0 = row0;
     d.row1 = row1;
+    d.stripe_n = cfg->stripe_count > 1 ? cfg->stripe_count : 1;
+    d.stripe_i = cfg->stripe_count > 1 ? cfg->stripe_index : 0;
 
     DeviceGuard guard(cfg->device);
     int rc = [&]() -> int {
@@ -402,7 +418,8 @@ int par_rebuild_grid(par_ctx* c) {
 // into up to kMaxChunks row chunks (whole tile rows) and the D2H copy of chunk k overlaps the
 // rendering of chunk k+1 on a second stream — at 4K the 33 MB readback takes about as long as
 // the kernels, so the drop-in call is roughly max(render, copy) instead of their sum.
-static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4* d_out, par_color* host_out) {
+static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4* d_out, par_color* host_out,
+                       bool striped_out = false) {
     if (!c || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
         return fail(PAR_ERR_INVALID_ARG, "par_render: bad argument (at most 64 lights)%s%s");
     if (!c->scene_set || c->n_sprites == 0)
@@ -431,31 +448,41 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     sp.n_lights = n_lights;
     sp.ambient = c->ambient;
     sp.phase_cycles = c->d_phase_cycles;  // NULL unless par_debug_phase_timing enabled it
+    sp.out_stripe_T = striped_out ? (d.HH + d.stripe_n - 1) / d.stripe_n : 0;
     memset(sp.lights, 0, sizeof sp.lights);
     for (int l = 0; l < n_lights; l++)
         sp.lights[l] = make_short4(lights[l].x, lights[l].y, lights[l].z, lights[l].radius);
 
     const int tile0 = d.row0 / kBin, tile1 = (d.row1 + kBin - 1) / kBin;
     int n_chunks = 1;
-    if (host_out && tile1 - tile0 >= 4 * kMaxChunks) n_chunks = kMaxChunks;  // >= 640 rows
+    if (host_out && d.stripe_n == 1 && tile1 - tile0 >= 4 * kMaxChunks) n_chunks = kMaxChunks;  // >= 640 rows
     PAR_CUDA(cudaEventRecord(c->ev_f0, c->stream));
     for (int k = 0; k < n_chunks; k++) {
         const int ta = tile0 + (tile1 - tile0) * k / n_chunks, tb = tile0 + (tile1 - tile0) * (k + 1) / n_chunks;
         const int ra = ta * kBin > d.row0 ? ta * kBin : d.row0, rb = tb * kBin < d.row1 ? tb * kBin : d.row1;
         pp.d.row0 = sp.d.row0 = ra;
         pp.d.row1 = sp.d.row1 = rb;
-        pp.tile_row_first = sp.tile_row_first = ta;
+        int first_owned, n_owned;
+        owned_tile_rows(pp.d, first_owned, n_owned);
+        pp.tile_row_first = sp.tile_row_first = first_owned;
         PAR_CUDA(cudaEventRecord(c->ev_chunk[k][0], c->stream));
         PAR_CUDA(launch_primary(pp, c->stream));
         PAR_CUDA(cudaEventRecord(c->ev_chunk[k][1], c->stream));
         PAR_CUDA(launch_shade(sp, c->stream));
         PAR_CUDA(cudaEventRecord(c->ev_chunk[k][2], c->stream));
-        if (host_out) {
+        if (host_out && d.stripe_n == 1) {
             const size_t first = (size_t)ra * d.W, count = (size_t)(rb - ra) * d.W;
             cudaStream_t cs = n_chunks > 1 ? c->copy_stream : c->stream;
             if (n_chunks > 1) PAR_CUDA(cudaStreamWaitEvent(cs, c->ev_chunk[k][2], 0));
             PAR_CUDA(cudaMemcpyAsync(host_out + first, d_out + first, sizeof(par_color) * count,
                                      cudaMemcpyDeviceToHost, cs));
+        } else if (host_out) {  // only the owned stripes, each clipped to the band
+            for (int t = first_owned, q = 0; q < n_owned; q++, t += d.stripe_n) {
+                const int sa = t * kBin > ra ? t * kBin : ra, sb = (t + 1) * kBin < rb ? (t + 1) * kBin : rb;
+                const size_t first = (size_t)sa * d.W, count = (size_t)(sb - sa) * d.W;
+                PAR_CUDA(cudaMemcpyAsync(host_out + first, d_out + first, sizeof(par_color) * count,
+                                         cudaMemcpyDeviceToHost, c->stream));
+            }
         }
     }
     PAR_CUDA(cudaEventRecord(c->ev_f2, c->stream));
@@ -474,6 +501,31 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
 int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d_rgba) {
     return render_impl(c, lights, n_lights, d_rgba ? static_cast<uchar4*>(d_rgba) : (c ? c->d_frame : nullptr),
                        nullptr);
+}
+
+size_t par_staging_bytes(const par_ctx* c) {
+    if (!c) return 0;
+    const size_t T = (size_t)(c->d.HH + c->d.stripe_n - 1) / c->d.stripe_n;
+    return (size_t)c->d.stripe_n * T * kBin * c->d.W * sizeof(par_color);
+}
+
+int par_render_device_striped(par_ctx* c, const par_light* lights, int n_lights, void* d_staging) {
+    if (!c || !d_staging) return fail(PAR_ERR_INVALID_ARG, "par_render_device_striped: null argument%s%s");
+    if (c->d.row0 != 0 || c->d.row1 != c->d.H)
+        return fail(PAR_ERR_INVALID_ARG, "par_render_device_striped: the context must cover the whole frame%s%s");
+    return render_impl(c, lights, n_lights, static_cast<uchar4*>(d_staging), nullptr, true);
+}
+
+int par_unstripe_device(par_ctx* c, const void* d_staging, void* d_rgba) {
+    if (!c || !d_staging || !d_rgba) return fail(PAR_ERR_INVALID_ARG, "par_unstripe_device: null argument%s%s");
+    DeviceGuard guard(c->cfg.device);
+    const ViewDims& d = c->d;
+    const int W4 = d.W / 4, T = (d.HH + d.stripe_n - 1) / d.stripe_n;
+    const size_t n = (size_t)W4 * d.H;
+    k_unstripe<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(static_cast<const uint4*>(d_staging),
+                                                                    static_cast<uint4*>(d_rgba), W4, d.H, d.stripe_n, T);
+    PAR_CUDA(cudaGetLastError());
+    return PAR_OK;
 }
 
 void* par_device_frame(par_ctx* c) { return c ? c->d_frame : nullptr; }
@@ -517,7 +569,17 @@ int par_get_stats(par_ctx* c, par_stats* st) {
     st->n_entities = c->n_entities;
     st->n_survivors = c->h_ctr->n_survivors;
     st->n_inserts = c->h_ctr->n_inserts;
-    st->rays = (uint64_t)(c->d.row1 - c->d.row0) * c->d.W * (1 + (uint64_t)c->last_n_lights);
+    uint64_t rows = 0;
+    {
+        int first, count;
+        owned_tile_rows(c->d, first, count);
+        for (int t = first, q = 0; q < count; q++, t += c->d.stripe_n) {
+            const int a = t * kBin > c->d.row0 ? t * kBin : c->d.row0;
+            const int b = (t + 1) * kBin < c->d.row1 ? (t + 1) * kBin : c->d.row1;
+            rows += (uint64_t)(b - a);
+        }
+    }
+    st->rays = rows * c->d.W * (1 + (uint64_t)c->last_n_lights);
     return PAR_OK;
 }
 

@@ -28,7 +28,17 @@ struct ViewDims {
     int HW, HH, HL;  // hash_width / hash_height / hash_length (alternative.cpp:120-122)
     int V;           // hash_volume
     int row0, row1;  // band rendered by this context
+    int stripe_n;    // >= 1: only tile rows t with t % stripe_n == stripe_i are rendered
+    int stripe_i;    //       (40-row stripes interleaved over ranks: load balance)
 };
+
+// Tile rows [first, first + count*stripe_n) step stripe_n owned by this context within its band.
+__host__ __device__ __forceinline__ void owned_tile_rows(const ViewDims& d, int& first, int& count) {
+    const int t0 = d.row0 / kBin, t1 = (d.row1 + kBin - 1) / kBin;  // band's tile rows [t0, t1)
+    const int n = d.stripe_n > 1 ? d.stripe_n : 1, i = d.stripe_n > 1 ? d.stripe_i : 0;
+    first = t0 + ((i - t0) % n + n) % n;
+    count = first < t1 ? (t1 - first + n - 1) / n : 0;
+}
 
 // alternative.cpp:180-182
 __host__ __device__ __forceinline__ int flat_bin(const ViewDims& d, int x, int y, int z) {

@@ -26,7 +26,7 @@ struct PrimaryParams {
     const int* atlas_depth;  // [n_sprites][800]
     int n_sprites;
     int4* gbuf;
-    int tile_row_first;  // first tile row (bin_y) of the band
+    int tile_row_first;  // first owned tile row (bin_y); the next ones are stripe_n apart
 };
 size_t primary_smem_bytes(const ViewDims& d, int n_sprites);
 cudaError_t configure_primary(size_t smem);  // per device, before the first launch
@@ -48,6 +48,7 @@ struct ShadeParams {
     int n_lights;
     float ambient;
     int tile_row_first;
+    int out_stripe_T;  // 0: raster output; T > 0: stripe-major staging, T stripes per rank
     unsigned long long* phase_cycles;  // optional debug instrumentation: 16 counters (NULL in production)
     short4 lights[kMaxLights];         // x, y, z, radius (alternative.cpp:619-622)
 };

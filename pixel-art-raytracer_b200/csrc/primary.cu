@@ -36,7 +36,7 @@ k_primary(PrimaryParams p) {
 
     const int tid = threadIdx.x;
     const int bx = blockIdx.x % d.HW;
-    const int ty = p.tile_row_first + blockIdx.x / d.HW;
+    const int ty = p.tile_row_first + (blockIdx.x / d.HW) * max(d.stripe_n, 1);
 
     // 1a. counts of the column (the reference's wrapping count is cnt & 7)
     for (int bz = tid; bz < d.HL; bz += blockDim.x)
@@ -133,7 +133,8 @@ cudaError_t configure_primary(size_t smem) {
 
 cudaError_t launch_primary(const PrimaryParams& p, cudaStream_t s) {
     const ViewDims& d = p.d;
-    int tile_rows = (d.row1 + kBin - 1) / kBin - d.row0 / kBin;
+    int first, tile_rows;
+    owned_tile_rows(d, first, tile_rows);
     if (tile_rows <= 0) return cudaSuccess;
     size_t smem = primary_smem_bytes(d, p.n_sprites);
     k_primary<<<tile_rows * d.HW, kTileThreads, smem, s>>>(p);

@@ -188,7 +188,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
     const ViewDims& d = p.d;
     const int tid = threadIdx.x, lane = tid & 31;
     const int bx = blockIdx.x % d.HW;
-    const int ty = p.tile_row_first + blockIdx.x / d.HW;
+    const int ty = p.tile_row_first + (blockIdx.x / d.HW) * max(d.stripe_n, 1);
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
     const int n_lights = p.n_lights;
 
@@ -551,7 +551,9 @@ k_shade(const __grid_constant__ ShadeParams p) {
         const int j = ty * kBin + v / (kBin / 4);
         if (j < ra || j >= rb) continue;
         const uint4 px = *reinterpret_cast<const uint4*>(&s.out[4 * v]);
-        *reinterpret_cast<uint4*>(&p.out[(size_t)j * d.W + bx * kBin + 4 * (v % (kBin / 4))]) = px;
+        // raster row, or the row's slot in the stripe-major staging frame (rank-contiguous)
+        const int jo = p.out_stripe_T ? ((ty % d.stripe_n) * p.out_stripe_T + ty / d.stripe_n) * kBin + (j - ty * kBin) : j;
+        *reinterpret_cast<uint4*>(&p.out[(size_t)jo * d.W + bx * kBin + 4 * (v % (kBin / 4))]) = px;
     }
 }
 
@@ -564,7 +566,8 @@ cudaError_t configure_shade() {
 
 cudaError_t launch_shade(const ShadeParams& p, cudaStream_t st) {
     const ViewDims& d = p.d;
-    int tile_rows = (d.row1 + kBin - 1) / kBin - d.row0 / kBin;
+    int first, tile_rows;
+    owned_tile_rows(d, first, tile_rows);
     if (tile_rows <= 0) return cudaSuccess;
     k_shade<<<tile_rows * d.HW, kThreads, sizeof(ShadeSmem), st>>>(p);
     return cudaGetLastError();

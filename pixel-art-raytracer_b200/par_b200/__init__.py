@@ -37,6 +37,7 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_multi_context", "par_multi_set_atlas", "par_multi_set_scene", "par_multi_render",
            "par_multi_last_error", "par_sync", "par_alloc_host", "par_free_host", "par_set_atlas", "par_set_scene",
            "par_rebuild_grid", "par_render", "par_render_device", "par_device_frame",
+           "par_render_device_striped", "par_staging_bytes", "par_unstripe_device",
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
            "par_debug_phase_timing",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
@@ -46,7 +47,8 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
 class Config(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("length", C.c_int32),
                 ("device", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
-                ("ambient", C.c_float), ("reserved", C.c_int32 * 5)]
+                ("ambient", C.c_float), ("stripe_count", C.c_int32), ("stripe_index", C.c_int32),
+                ("reserved", C.c_int32 * 3)]
 
 
 class Stats(C.Structure):
@@ -105,6 +107,10 @@ def lib():
         L.par_rebuild_grid.argtypes = [vp]
         L.par_render.argtypes = [vp, vp, i32, vp, vp, C.POINTER(Stats)]
         L.par_render_device.argtypes = [vp, vp, i32, vp]
+        L.par_render_device_striped.argtypes = [vp, vp, i32, vp]
+        L.par_staging_bytes.argtypes = [vp]
+        L.par_staging_bytes.restype = C.c_size_t
+        L.par_unstripe_device.argtypes = [vp, vp, vp]
         L.par_device_frame.argtypes = [vp]
         L.par_device_frame.restype = vp
         L.par_get_gbuffer.argtypes = [vp, vp, vp]
@@ -208,10 +214,11 @@ class Renderer:
         render(lights)        <- trace_hash_for_pixel + shading loop, returns Color[H][W]
     """
 
-    def __init__(self, W, H, L, device=0, row_begin=0, row_end=0, ambient=0.0):
+    def __init__(self, W, H, L, device=0, row_begin=0, row_end=0, ambient=0.0, stripe_count=0,
+                 stripe_index=0):
         self.W, self.H, self.L = W, H, L
         self._h = C.c_void_p()
-        cfg = Config(W, H, L, device, row_begin, row_end, ambient)
+        cfg = Config(W, H, L, device, row_begin, row_end, ambient, stripe_count, stripe_index)
         self.row_begin = row_begin
         self.row_end = row_end if (row_begin or row_end) else H
         _check(lib().par_create(C.byref(self._h), C.byref(cfg)))
@@ -266,6 +273,17 @@ class Renderer:
         """par_render_device: asynchronous, into HBM (own frame buffer when d_rgba is None)."""
         lights = np.ascontiguousarray(lights, LIGHT)
         _check(lib().par_render_device(self._h, _p(lights), len(lights), d_rgba))
+
+    def render_device_striped(self, lights, d_staging: int):
+        """This context's stripes, stripe-major, into a staging frame (see par.h)."""
+        lights = np.ascontiguousarray(lights, LIGHT)
+        _check(lib().par_render_device_striped(self._h, _p(lights), len(lights), d_staging))
+
+    def staging_bytes(self) -> int:
+        return int(lib().par_staging_bytes(self._h))
+
+    def unstripe_device(self, d_staging: int, d_rgba: int):
+        _check(lib().par_unstripe_device(self._h, d_staging, d_rgba))
 
     def device_frame(self) -> int:
         return lib().par_device_frame(self._h)

@@ -1,8 +1,12 @@
-"""Row-band partition of a frame over ranks and the in-place frame gather.
+"""Partition of a frame over ranks and the in-place frame gather.
 
-One process per GPU: rank r renders rows [r*H/N, (r+1)*H/N) in place into a full-size frame
-and a single in-place all-gather completes the frame on every rank.  Backend agnostic
-(nccl on GPUs over NVLink, gloo on CPU for the host-logic tests)."""
+Two partitions, one process per GPU, backend agnostic (nccl over NVLink on GPUs, gloo on CPU
+for the host-logic tests):
+  * stripes (default for rendering): rank r owns the 40-row tile rows t with t % N == r and
+    writes them stripe-major into a staging frame [N][T][40*W*4 bytes], T = ceil(H/40/N), so
+    its output is contiguous; one in-place all-gather + an un-stripe copy give the raster frame.
+    Interleaving balances the strongly row-dependent cost of the shadow walks.
+  * bands: rank r owns rows [r*H/N, (r+1)*H/N) in place in the raster frame."""
 from __future__ import annotations
 
 
@@ -28,3 +32,30 @@ def gather_bands(frame, W: int, H: int, world: int, rank: int, group=None) -> No
         for b in range(world):
             r0, r1 = band_rows(H, world, b)
             dist.broadcast(frame[r0 * row_bytes:r1 * row_bytes], src=b, group=group)
+
+
+def stripes_per_rank(H: int, world: int) -> int:
+    """T: 40-row stripes per rank in the stripe-major staging frame (the last ones may be padding)."""
+    return (H // 40 + world - 1) // world
+
+
+def owned_rows(H: int, world: int, rank: int) -> list[tuple[int, int]]:
+    """Raster row ranges of the stripes rank `rank` renders."""
+    return [(t * 40, t * 40 + 40) for t in range(rank, H // 40, world)]
+
+
+def gather_stripes(staging, world: int, rank: int, group=None) -> None:
+    """staging: flat uint8 tensor [world][T][40*W*4] whose block `rank` is valid; in-place all-gather."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+    block = staging.numel() // world
+    dist.all_gather_into_tensor(staging, staging[rank * block:(rank + 1) * block], group=group)
+
+
+def unstripe(staging, W: int, H: int, world: int):
+    """Stripe-major staging frame -> raster frame (flat uint8 tensor of H*W*4 bytes); torch ops only
+    (the GPU path uses par_unstripe_device, this is the reference implementation for tests)."""
+    T = stripes_per_rank(H, world)
+    stripe = 40 * W * 4
+    return staging.view(world, T, stripe).permute(1, 0, 2).reshape(-1)[: H * W * 4]

@@ -30,6 +30,37 @@ def _worker(rank, world, port, W, H, L, out_dir):
     dist.destroy_process_group()
 
 
+def _stripe_worker(rank, world, port, W, H, L, out_dir):
+    for p in (ROOT, PKG):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import oracle as O
+    from par_b200.bands import gather_stripes, owned_rows, stripes_per_rank, unstripe
+    boxes, lights = O.scene_synthetic(W, H, L, n=600, n_lights=3)
+    T, stripe = stripes_per_rank(H, world), 40 * W * 4
+    staging = torch.zeros(world * T * stripe, dtype=torch.uint8)
+    for k, (r0, r1) in enumerate(owned_rows(H, world, rank)):  # what par_render_device_striped writes
+        rows = O.render(W, H, L, boxes, lights, row0=r0, row1=r1, want_gbuf=False, want_texel=False)["rgba"][r0:r1]
+        staging[(rank * T + k) * stripe:(rank * T + k + 1) * stripe] = torch.from_numpy(rows.view(np.uint8).reshape(-1).copy())
+    gather_stripes(staging, world, rank)
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), unstripe(staging, W, H, world).numpy())
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_stripe_gather(oracle, tmp_path, world):
+    """The default multi-GPU partition: interleaved stripes, stripe-major staging, in-place
+    all-gather, un-stripe (8 tile rows over 3 ranks: padded staging)."""
+    W, H, L = 480, 320, 320
+    port = 29700 + os.getpid() % 2000 + world
+    mp.spawn(_stripe_worker, args=(world, port, W, H, L, str(tmp_path)), nprocs=world, join=True)
+    boxes, lights = oracle.scene_synthetic(W, H, L, n=600, n_lights=3)
+    want = oracle.render(W, H, L, boxes, lights, want_gbuf=False, want_texel=False)["rgba"].view(np.uint8).reshape(-1)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / f"rank{r}.npy"), want), f"rank {r}"
+
+
 @pytest.mark.parametrize("world,H", [(2, 320), (3, 320)])
 def test_band_gather(oracle, tmp_path, world, H):
     W, L = 480, 320

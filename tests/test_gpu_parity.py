@@ -305,6 +305,48 @@ def test_row_bands_reassemble(par):
     assert gout.tobytes() == gfull.tobytes()
 
 
+@pytest.mark.parametrize("n", [2, 3, 8])
+def test_stripes_reassemble(par, n):
+    """Interleaved 40-row stripes (the multi-GPU partition): raster output of every stripe set,
+    and the stripe-major staging frame + un-stripe copy, both give the one-context frame."""
+    import torch
+    W, H, L = 640, 480, 480  # 12 tile rows: not a multiple of 8 -> padded staging
+    boxes, lights = par.scene_synthetic(W, H, L, n=1500, n_lights=5)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        full, _ = r.render(lights)
+    out = np.zeros((H, W), par.COLOR)
+    staging = None
+    rays = 0
+    for i in range(n):
+        with par.Renderer(W, H, L, stripe_count=n, stripe_index=i) as r:
+            r.set_atlas()
+            r.set_scene(boxes)
+            part = np.zeros((H, W), par.COLOR)
+            _, st = r.render(lights, out=part)
+            rays += st["rays"]
+            own = np.zeros(H, bool)
+            for t in range(i, H // 40, n):
+                own[t * 40:t * 40 + 40] = True
+            assert not _u32(part[~own]).any()
+            out[own] = part[own]
+            if staging is None:
+                staging = torch.zeros(r.staging_bytes(), dtype=torch.uint8, device="cuda")
+            r.render_device_striped(lights, staging.data_ptr())
+            r.sync()
+            last = r
+            if i == n - 1:
+                raster = torch.zeros(H * W * 4, dtype=torch.uint8, device="cuda")
+                r.unstripe_device(staging.data_ptr(), raster.data_ptr())
+                r.sync()
+    assert rays == W * H * 6
+    assert np.array_equal(_u32(out), _u32(full))
+    assert np.array_equal(raster.cpu().numpy(), full.view(np.uint8).reshape(-1))
+    from par_b200.bands import unstripe
+    assert np.array_equal(unstripe(staging, W, H, n).cpu().numpy(), full.view(np.uint8).reshape(-1))
+
+
 def test_determinism_and_rebuild_idempotence(par):
     W, H, L = 1920, 1080, 1080
     boxes, lights = par.scene_synthetic(W, H, L, n=10000, n_lights=8)
