@@ -115,6 +115,8 @@ struct par_ctx {
     bool scene_set = false, frame_valid = false, build_timed = false, frame_timed = false;
     int launches_build = 0, launches_frame = 0, last_n_lights = 0;
     float ambient = 0.25f;
+    float last_kernel_ms = 0.f;  // primary + shade of the previous par_render (pipelining heuristic)
+    int debug_flags = 0;  // from the PAR_DEBUG_FLAGS environment variable (developer A/B switches)
 };
 
 namespace {
@@ -196,6 +198,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
     if (!c) return fail(PAR_ERR_OUT_OF_MEMORY, "par_create: host allocation failed%s%s");
     c->cfg = *cfg;
     c->ambient = cfg->ambient == 0.f ? 0.25f : cfg->ambient;
+    if (const char* e = getenv("PAR_DEBUG_FLAGS")) c->debug_flags = atoi(e);
     ViewDims& d = c->d;
     d.W = cfg->width;
     d.H = cfg->height;
@@ -448,6 +451,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     sp.n_lights = n_lights;
     sp.ambient = c->ambient;
     sp.phase_cycles = c->d_phase_cycles;  // NULL unless par_debug_phase_timing enabled it
+    sp.debug_flags = c->debug_flags;
     sp.out_stripe_T = striped_out ? (d.HH + d.stripe_n - 1) / d.stripe_n : 0;
     memset(sp.lights, 0, sizeof sp.lights);
     for (int l = 0; l < n_lights; l++)
@@ -455,7 +459,16 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
 
     const int tile0 = d.row0 / kBin, tile1 = (d.row1 + kBin - 1) / kBin;
     int n_chunks = 1;
-    if (host_out && d.stripe_n == 1 && tile1 - tile0 >= 4 * kMaxChunks) n_chunks = kMaxChunks;  // >= 640 rows
+    if (host_out && d.stripe_n == 1 && tile1 - tile0 >= 4 * kMaxChunks) {  // >= 640 rows
+        // Pipelining costs kernel efficiency (partial waves per chunk), so it is used only when
+        // the readback is not small next to the kernels (measured on the previous frame) and
+        // the destination is page-locked (a pageable copy would block the launching thread).
+        cudaPointerAttributes attr;
+        const bool pinned = cudaPointerGetAttributes(&attr, host_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const float copy_ms = (float)(d.row1 - d.row0) * d.W * 4.f / 50e6f;  // ~50 GB/s PCIe gen5
+        if (pinned && c->last_kernel_ms > 0.f && c->last_kernel_ms < 2.5f * copy_ms) n_chunks = kMaxChunks;
+    }
     PAR_CUDA(cudaEventRecord(c->ev_f0, c->stream));
     for (int k = 0; k < n_chunks; k++) {
         const int ta = tile0 + (tile1 - tile0) * k / n_chunks, tb = tile0 + (tile1 - tile0) * (k + 1) / n_chunks;
@@ -592,7 +605,10 @@ int par_render(par_ctx* c, const par_light* lights, int n_lights, par_color* out
     if (out_gbuf && (rc = expand_gbuffer(c, out_gbuf, nullptr)) != PAR_OK) return rc;
     PAR_CUDA(cudaStreamSynchronize(c->stream));
     if ((rc = check_scene_flag(c)) != PAR_OK) return rc;
-    if (stats) return par_get_stats(c, stats);
+    par_stats st;
+    if ((rc = par_get_stats(c, &st)) != PAR_OK) return rc;
+    c->last_kernel_ms = st.ms_primary + st.ms_shade;
+    if (stats) *stats = st;
     return PAR_OK;
 }
 

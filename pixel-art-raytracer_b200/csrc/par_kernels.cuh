@@ -49,6 +49,7 @@ struct ShadeParams {
     float ambient;
     int tile_row_first;
     int out_stripe_T;  // 0: raster output; T > 0: stripe-major staging, T stripes per rank
+    int debug_flags;   // bit 0: disable the shaft cull (A/B measurements only)
     unsigned long long* phase_cycles;  // optional debug instrumentation: 16 counters (NULL in production)
     short4 lights[kMaxLights];         // x, y, z, radius (alternative.cpp:619-622)
 };

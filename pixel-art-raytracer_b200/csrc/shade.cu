@@ -45,7 +45,6 @@ constexpr int kThreads = PAR_SHADE_THREADS;   // CTA size of k_shade (a multiple
 constexpr int kListCap = PAR_SHADE_LIST_CAP;  // boxes in the shared list (lo/hi float4 pairs, 32 B each)
 constexpr int kHashSize = 2 * kListCap;       // de-duplication set
 constexpr int kHashBits = kListCap == 1024 ? 11 : kListCap == 512 ? 10 : 9;
-constexpr int kOccCap = kListCap;             // occupied probed bins per round
 constexpr int kSegMax = 16;                   // (light, step range) segments per round
 constexpr int kMaxRun = 32;                   // most walk steps per phase-1 thread
 constexpr int kScratchRows = kListCap * 8 / kThreads;  // ints per thread in the idle box list
@@ -72,7 +71,7 @@ struct Segment {
 struct ShadeSmem {
     float4 list[2 * kListCap];
     unsigned hash[kHashSize];
-    uint2 occ[kOccCap];  // .x = flat bin, .y = segment << 8 | count
+    unsigned entry[kListCap];  // candidate slots found by the walk: segment << 28 | (flat bin * 8 + slot)
     unsigned out[kTilePixels];  // finished RGBA8; between rounds of a split group: the fp32 acc bits
     unsigned short pix[kTilePixels];
     unsigned char sh[kTilePixels];
@@ -80,7 +79,7 @@ struct ShadeSmem {
     int warp_scan[kWarps];
     int scan_total;
     int group;
-    int n_occ;
+    int n_entries;
     int n_items;
     int run;  // walk steps per phase-1 thread this round
 };
@@ -145,6 +144,33 @@ __device__ __forceinline__ bool any_box_hit(const float4* __restrict__ boxes, in
         if (hit && __float_as_int(lo.w) != self) return true;  // quirk Q17: own entity never shadows
     }
     return false;
+}
+
+// Exact-output "shaft" cull of a candidate box for a whole pixel group: all ray origins of the
+// group lie in the integer box [ol, oh] (per axis), all rays go through the light L.  In real
+// arithmetic a pixel's line hits the box iff the per-axis parameter intervals
+// [min, max]{(lo_a - o_a)/(L_a - o_a), (hi_a - o_a)/(L_a - o_a)} intersect (the reference's
+// slab test up to the positive scale |L - o|_1).  Each endpoint is monotonic in o_a, so its hull
+// over the group is attained at the interval ends; if the hulls of the three axes do not
+// intersect — with a 1e-4 relative margin, three orders of magnitude above the fp32 error of
+// the reference's formula — no pixel of the group can pass the reference's test and the box is
+// dropped.  Axes on which some pixel may have a zero direction component (0 in [L-oh, L-ol])
+// impose no constraint, which also covers every NaN/inf case (quirk Q13) conservatively.
+__device__ __forceinline__ bool shaft_may_hit(const float lo[3], const float hi[3], const float L[3],
+                                              const float ol[3], const float oh[3]) {
+    float smin = -INFINITY, smax = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float dl = L[a] - oh[a], dh = L[a] - ol[a];
+        if (dl <= 0.f && dh >= 0.f) continue;
+        // approximate reciprocals (2 ulp) are plenty under the 1e-4 margin
+        const float rl = __fdividef(1.f, dl), rh = __fdividef(1.f, dh);
+        const float v0 = (lo[a] - ol[a]) * rh, v1 = (lo[a] - oh[a]) * rl;
+        const float v2 = (hi[a] - ol[a]) * rh, v3 = (hi[a] - oh[a]) * rl;
+        smin = fmaxf(smin, fminf(fminf(v0, v1), fminf(v2, v3)));
+        smax = fminf(smax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
+    }
+    return !(smin > smax + 1e-4f * (1.f + fabsf(smin) + fabsf(smax)));
 }
 
 // Block-wide exclusive scan of one int per thread (10 warps); *total gets the sum.
@@ -256,6 +282,25 @@ k_shade(const __grid_constant__ ShadeParams p) {
         // start bin of every pixel of the group (alternative.cpp:724-727, quirk Q11)
         const int start = flat_bin(d, bx, ty, group);
 
+        // Integer bounds of the group's ray origins (alternative.cpp:720-722), for the shaft cull:
+        // x = pixel column; z / 40 == group with C truncation; y = (H - row) - z (quirk Q11).
+        float org_lo[3], org_hi[3];
+        bool can_cull;
+        {
+            const int zl = group > 0 ? group * kBin : group * kBin - (kBin - 1);
+            const int zh = group >= 0 ? group * kBin + (kBin - 1) : group * kBin;
+            const int wl = d.H - (ty * kBin + kBin - 1), wh = d.H - ty * kBin;
+            const int yl = wl - zh, yh = wh - zl;
+            org_lo[0] = (float)(bx * kBin);
+            org_hi[0] = (float)(bx * kBin + kBin - 1);
+            org_lo[1] = (float)yl;
+            org_hi[1] = (float)yh;
+            org_lo[2] = (float)zl;
+            org_hi[2] = (float)zh;
+            // the origin is cast to short in the reference: only cull when nothing can wrap
+            can_cull = zl >= -32768 && zh <= 32767 && yl >= -32768 && yh <= 32767 && !(p.debug_flags & 1);
+        }
+
         // ---- rounds over (light, step range) segments ----
         int l_cur = 0, ka_cur = 0;  // next unprocessed step of light l_cur
         int kb_try = -1;            // trial end of segment 0 (-1 = the whole walk)
@@ -299,7 +344,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 }
                 s.n_items = items;
                 s.run = run;
-                s.n_occ = 0;
+                s.n_entries = 0;
             }
             __syncthreads();
             mark(kPhSetup);
@@ -374,27 +419,34 @@ k_shade(const __grid_constant__ ShadeParams p) {
                                 boxes += c[u];
                             }
                     }
-                    if (found) {
-                        const int o = atomicAdd(&s.n_occ, found);
+                    if (found) {  // one descriptor per candidate slot, so that phase 2 runs with dense lanes
+                        int o = atomicAdd(&s.n_entries, boxes);
                         atomicAdd(&s.seg[q].count, boxes);
                         for (int j = 0; j < found; j++) {
                             const int e = scratch[j * kThreads + tid];
-                            if (o + j < kOccCap) s.occ[o + j] = make_uint2((unsigned)(e >> 3), (unsigned)q << 8 | (e & 7));
+                            for (int slot = 0; slot < (e & 7); slot++, o++)
+                                if (o < kListCap) s.entry[o] = (unsigned)q << 28 | (unsigned)((e >> 3) * kSlots + slot);
                         }
                     }
                 }
             }
             __syncthreads();
             mark(kPhWalk);
-            const int n_occ_all = s.n_occ, n_occ = min(n_occ_all, kOccCap);
+            const int n_entries_all = s.n_entries, n_entries = min(n_entries_all, kListCap);
             // D. how many leading segments fit the box list?  (every thread, redundantly)
             int n_fit = 0;
-            if (n_occ_all <= kOccCap) {
+            {
                 int total = 0;
                 while (n_fit < nseg && total + s.seg[n_fit].count <= kListCap) {
                     total += s.seg[n_fit].count;
                     n_fit++;
                 }
+            }
+            if (n_fit > 0 && n_fit < nseg && n_entries_all > kListCap) {
+                // descriptors of the fitting segments may have been dropped: redo the walk for
+                // exactly those segments (they fit, so nothing is dropped next time)
+                nseg_try = n_fit;
+                continue;
             }
             if (tid < n_fit) {  // base of segment tid in the box list
                 int base = 0;
@@ -412,15 +464,13 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 continue;
             }
 
-            // E. phase 2: gather + de-duplicate the boxes of the fitting segments
-            for (int o = tid; o < n_occ; o += kThreads) {
-              const uint2 e = s.occ[o];
-              const int c = e.y & 0xff, q = e.y >> 8;
-              if (q >= n_fit) continue;
-              int base = 0;
-              for (int r = 0; r < q; r++) base += s.seg[r].count;
-              for (int slot = 0; slot < c; slot++) {
-                const int ent = p.ids[e.x * kSlots + slot];
+            // E. phase 2: one lane per candidate slot: entity -> de-duplicate -> box -> shaft cull ->
+            // the segment's part of the box list
+            for (int e0 = tid; e0 < n_entries; e0 += kThreads) {
+                const unsigned desc = s.entry[e0];
+                const int q = desc >> 28;
+                if (q >= n_fit) continue;
+                const int ent = p.ids[desc & 0x0fffffffu];
                 const unsigned key = (unsigned)q << 26 | (unsigned)ent;
                 unsigned h = (key * 2654435761u) >> (32 - kHashBits);
                 bool fresh_key;
@@ -434,14 +484,32 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 }
                 if (!fresh_key) continue;
                 const Box b = unpack_box(p.boxes[ent]);
+                if (can_cull) {
+                    const short4 lt = p.lights[s.seg[q].light];
+                    const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
+                    const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
+                    const float lp[3] = {(float)lt.x, (float)lt.y, (float)lt.z};
+                    if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
+                }
+                int base = 0;
+                for (int r = 0; r < q; r++) base += s.seg[r].count;
                 const int at = base + atomicAdd(&s.seg[q].fill, 1);
                 s.list[2 * at] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(ent));
                 s.list[2 * at + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
                                                  (float)(b.pz + b.ez), 0.f);
-              }
             }
             __syncthreads();
             mark(kPhGather);
+            if (p.phase_cycles && tid == 0) {  // debug: candidate boxes found / kept after de-dup + cull
+                unsigned long long found = 0, kept = 0;
+                for (int q = 0; q < n_fit; q++) {
+                    found += s.seg[q].count;
+                    kept += s.seg[q].fill;
+                }
+                atomicAdd(&p.phase_cycles[10], found);
+                atomicAdd(&p.phase_cycles[11], kept);
+                atomicAdd(&p.phase_cycles[12], (unsigned long long)npix * n_fit);
+            }
 
             // F. phase 3: one lane per pixel of the group
             const bool final_round = s.seg[n_fit - 1].light == n_lights - 1 &&

@@ -307,7 +307,9 @@ class Renderer:
         """Debug: per-phase cycle totals of k_shade since the last call (dict), then (re)arm."""
         out = np.zeros(16, np.uint64)
         _check(lib().par_debug_phase_timing(self._h, int(enable), _p(out)))
-        return {n: int(out[i]) for i, n in enumerate(self.PHASES)}
+        d = {n: int(out[i]) for i, n in enumerate(self.PHASES)}
+        d.update(boxes_found=int(out[10]), boxes_kept=int(out[11]), pixel_lights=int(out[12]))
+        return d
 
     def stats(self):
         st = Stats()
