@@ -71,7 +71,7 @@ struct Segment {
 struct ShadeSmem {
     float4 list[2 * kListCap];
     unsigned hash[kHashSize];
-    unsigned entry[kListCap];  // candidate slots found by the walk: segment << 28 | (flat bin * 8 + slot)
+    unsigned occ[kListCap];  // occupied bins found by the walk: segment << 28 | count << 25 | flat bin (< 2^25)
     unsigned out[kTilePixels];  // finished RGBA8; between rounds of a split group: the fp32 acc bits
     unsigned short pix[kTilePixels];
     unsigned char sh[kTilePixels];
@@ -79,7 +79,7 @@ struct ShadeSmem {
     int warp_scan[kWarps];
     int scan_total;
     int group;
-    int n_entries;
+    int n_occ;
     int n_items;
     int run;  // walk steps per phase-1 thread this round
 };
@@ -344,7 +344,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 }
                 s.n_items = items;
                 s.run = run;
-                s.n_entries = 0;
+                s.n_occ = 0;
             }
             __syncthreads();
             mark(kPhSetup);
@@ -419,20 +419,19 @@ k_shade(const __grid_constant__ ShadeParams p) {
                                 boxes += c[u];
                             }
                     }
-                    if (found) {  // one descriptor per candidate slot, so that phase 2 runs with dense lanes
-                        int o = atomicAdd(&s.n_entries, boxes);
+                    if (found) {
+                        const int o = atomicAdd(&s.n_occ, found);
                         atomicAdd(&s.seg[q].count, boxes);
                         for (int j = 0; j < found; j++) {
                             const int e = scratch[j * kThreads + tid];
-                            for (int slot = 0; slot < (e & 7); slot++, o++)
-                                if (o < kListCap) s.entry[o] = (unsigned)q << 28 | (unsigned)((e >> 3) * kSlots + slot);
+                            if (o + j < kListCap) s.occ[o + j] = (unsigned)q << 28 | (unsigned)(e & 7) << 25 | (unsigned)(e >> 3);
                         }
                     }
                 }
             }
             __syncthreads();
             mark(kPhWalk);
-            const int n_entries_all = s.n_entries, n_entries = min(n_entries_all, kListCap);
+            const int n_occ = s.n_occ;  // every occupied bin holds >= 1 box, so n_occ <= sum of counts
             // D. how many leading segments fit the box list?  (every thread, redundantly)
             int n_fit = 0;
             {
@@ -442,8 +441,8 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     n_fit++;
                 }
             }
-            if (n_fit > 0 && n_fit < nseg && n_entries_all > kListCap) {
-                // descriptors of the fitting segments may have been dropped: redo the walk for
+            if (n_fit > 0 && n_occ > kListCap) {
+                // bins of the fitting segments may have been dropped from the list: redo the walk for
                 // exactly those segments (they fit, so nothing is dropped next time)
                 nseg_try = n_fit;
                 continue;
@@ -464,39 +463,61 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 continue;
             }
 
-            // E. phase 2: one lane per candidate slot: entity -> de-duplicate -> box -> shaft cull ->
-            // the segment's part of the box list
-            for (int e0 = tid; e0 < n_entries; e0 += kThreads) {
-                const unsigned desc = s.entry[e0];
-                const int q = desc >> 28;
-                if (q >= n_fit) continue;
-                const int ent = p.ids[desc & 0x0fffffffu];
-                const unsigned key = (unsigned)q << 26 | (unsigned)ent;
-                unsigned h = (key * 2654435761u) >> (32 - kHashBits);
-                bool fresh_key;
-                for (;;) {
-                    const unsigned old = atomicCAS(&s.hash[h], kEmpty, key);
-                    if (old == kEmpty || old == key) {
-                        fresh_key = old == kEmpty;
-                        break;
+            // E. phase 2: one lane per candidate slot.  Each warp takes 32 occupied bins, scans their
+            // counts and expands them into (bin, slot) pairs with shuffles, so that the dependent
+            // loads (entity id -> box) run with dense lanes: entity -> de-duplicate -> box ->
+            // shaft cull -> the segment's part of the box list.
+            for (int ob = tid - lane; ob < n_occ; ob += kThreads) {
+                const unsigned mine = ob + lane < n_occ ? s.occ[ob + lane] : 0u;
+                const int my_c = (int)(mine >> 28) < n_fit ? (mine >> 25) & 7 : 0;
+                int incl = my_c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    const int t = t0 + lane;
+                    int src = 0;  // first lane whose inclusive prefix exceeds t
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int v = __shfl_sync(0xffffffffu, incl, src + step - 1);
+                        if (v <= t) src += step;
                     }
-                    h = (h + 1) & (kHashSize - 1);
+                    src = min(src, 31);
+                    const unsigned desc = __shfl_sync(0xffffffffu, mine, src);
+                    const int slot = t - (__shfl_sync(0xffffffffu, incl, src) - (int)((desc >> 25) & 7));
+                    if (t >= total) continue;
+                    const int q = desc >> 28;
+                    const int ent = p.ids[(desc & 0x1ffffffu) * kSlots + slot];
+                    const unsigned key = (unsigned)q << 26 | (unsigned)ent;
+                    unsigned h = (key * 2654435761u) >> (32 - kHashBits);
+                    bool fresh_key;
+                    for (;;) {
+                        const unsigned old = atomicCAS(&s.hash[h], kEmpty, key);
+                        if (old == kEmpty || old == key) {
+                            fresh_key = old == kEmpty;
+                            break;
+                        }
+                        h = (h + 1) & (kHashSize - 1);
+                    }
+                    if (!fresh_key) continue;
+                    const Box b = unpack_box(p.boxes[ent]);
+                    if (can_cull) {
+                        const short4 lt = p.lights[s.seg[q].light];
+                        const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
+                        const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
+                        const float lp[3] = {(float)lt.x, (float)lt.y, (float)lt.z};
+                        if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
+                    }
+                    int base = 0;
+                    for (int r = 0; r < q; r++) base += s.seg[r].count;
+                    const int at = base + atomicAdd(&s.seg[q].fill, 1);
+                    s.list[2 * at] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(ent));
+                    s.list[2 * at + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
+                                                     (float)(b.pz + b.ez), 0.f);
                 }
-                if (!fresh_key) continue;
-                const Box b = unpack_box(p.boxes[ent]);
-                if (can_cull) {
-                    const short4 lt = p.lights[s.seg[q].light];
-                    const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
-                    const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
-                    const float lp[3] = {(float)lt.x, (float)lt.y, (float)lt.z};
-                    if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
-                }
-                int base = 0;
-                for (int r = 0; r < q; r++) base += s.seg[r].count;
-                const int at = base + atomicAdd(&s.seg[q].fill, 1);
-                s.list[2 * at] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(ent));
-                s.list[2 * at + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
-                                                 (float)(b.pz + b.ez), 0.f);
             }
             __syncthreads();
             mark(kPhGather);
