@@ -378,6 +378,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     pz = pz + sz;
                 }
                 int x0 = (int)px, y0 = (int)py, z0 = (int)pz;
+                const int sxy = d.HH * d.HL;
                 while (k < k1) {
                     int n = 0;
                     for (int u = 0; u < 8 && k < k1 && n + 7 <= kScratchRows; u++, k++) {
@@ -385,17 +386,15 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         py = py + sy;
                         pz = pz + sz;
                         const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
-                        const int cx = x1 != x0, cy = y1 != y0, cz = z1 != z0;
                         // The 7 probes of a step are the bins {x0|x1} x {y0|y1} x {z0|z1} minus
-                        // "all old"; the all-old bin was the previous step's last probe (or the
-                        // start bin, which is skipped anyway: quirk Q16).
-#pragma unroll
-                        for (int mask = 1; mask < 8; mask++) {
-                            if (((mask & 1) && !cx) || ((mask & 2) && !cy) || ((mask & 4) && !cz))
-                                continue;  // same bin as the probe with that bit cleared
-                            const int f = flat_bin(d, (mask & 1) ? x1 : x0, (mask & 2) ? y1 : y0,
-                                                   (mask & 4) ? z1 : z0);
-                            if (f == start || f < 0 || f >= d.V) continue;  // Q16 / Q18
+                        // "all old" (the all-old bin was the previous step's last probe, or the
+                        // start bin, which is skipped anyway: quirk Q16).  Distinct bins among
+                        // them = the non-empty subsets of the axes whose bin changed.
+                        const int changed = (x1 != x0) | (y1 != y0) << 1 | (z1 != z0) << 2;
+                        const int fx0 = x0 * sxy, fx1 = x1 * sxy, fy0 = y0 * d.HL, fy1 = y1 * d.HL;
+                        for (int sub = changed; sub; sub = (sub - 1) & changed) {
+                            const int f = ((sub & 1) ? fx1 : fx0) + ((sub & 2) ? fy1 : fy0) + ((sub & 4) ? z1 : z0);
+                            if (f == start || (unsigned)f >= (unsigned)d.V) continue;  // Q16 / Q18
                             scratch[n * kThreads + tid] = f;
                             n++;
                         }
@@ -403,17 +402,18 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         y0 = y1;
                         z0 = z1;
                     }
+                    // the 4-bit counts of the sub-chunk, in batches of 8 independent loads
                     int found = 0, boxes = 0;
-                    for (int i = 0; i < n; i += 4) {
-                        int f[4], c[4];
+                    for (int i0 = 0; i0 < n; i0 += 8) {
+                        int f[8], c[8];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) f[u] = i + u < n ? scratch[(i + u) * kThreads + tid] : -1;
-#pragma unroll
-                        for (int u = 0; u < 4; u++)
+                        for (int u = 0; u < 8; u++) {
+                            f[u] = i0 + u < n ? scratch[(i0 + u) * kThreads + tid] : -1;
                             c[u] = f[u] >= 0 ? (__ldg(&p.occ4[f[u] >> 3]) >> ((f[u] & 7) * 4)) & 7 : 0;
+                        }
 #pragma unroll
-                        for (int u = 0; u < 4; u++)
-                            if (c[u]) {  // in-place compaction: found <= i + u
+                        for (int u = 0; u < 8; u++)
+                            if (c[u]) {  // in-place compaction: found <= i0 + u
                                 scratch[found * kThreads + tid] = f[u] << 3 | c[u];
                                 found++;
                                 boxes += c[u];
