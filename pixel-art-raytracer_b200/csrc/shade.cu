@@ -80,6 +80,7 @@ struct ShadeSmem {
     int scan_total;
     int group;
     int n_occ;
+    int org_min[3], org_max[3];  // actual bounds of the current group's ray origins (shaft cull)
     int n_items;
     int run;  // walk steps per phase-1 thread this round
 };
@@ -253,7 +254,11 @@ k_shade(const __grid_constant__ ShadeParams p) {
     int last_group = -0x7fffffff - 1;
     for (;;) {
         // ---- next group: the smallest start-bin z not yet processed in this tile ----
-        if (tid == 0) s.group = kNoGroup;
+        if (tid == 0) {
+            s.group = kNoGroup;
+            s.org_min[0] = s.org_min[1] = s.org_min[2] = 0x7fffffff;
+            s.org_max[0] = s.org_max[1] = s.org_max[2] = -0x7fffffff - 1;
+        }
         __syncthreads();
         mark(last_group == -0x7fffffff - 1 ? kPhLoad : kPhShade);
         int mine = kNoGroup;
@@ -275,31 +280,37 @@ k_shade(const __grid_constant__ ShadeParams p) {
         for (int m = 0; m < kPixPerThread; m++) my_n += (gz[m] == group);
         int pos = block_exclusive_scan(my_n, s);
         const int npix = s.scan_total;
+        int lo3[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi3[3] = {-0x7fffffff - 1, -0x7fffffff - 1, -0x7fffffff - 1};
 #pragma unroll
         for (int m = 0; m < kPixPerThread; m++)
-            if (gz[m] == group) s.pix[pos++] = (unsigned short)(m * kThreads + tid);
+            if (gz[m] == group) {
+                const int pidx = m * kThreads + tid;
+                s.pix[pos++] = (unsigned short)pidx;
+                // ray origin of this pixel (alternative.cpp:720-722), for the group's bounds
+                const int j = ty * kBin + pidx / kBin, i = bx * kBin + pidx % kBin;
+                const int4 g = __ldcs(&p.gbuf[(size_t)j * d.W + i]);
+                const int o3[3] = {i, g.y, g.z};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    lo3[a] = min(lo3[a], o3[a]);
+                    hi3[a] = max(hi3[a], o3[a]);
+                }
+            }
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                lo3[a] = min(lo3[a], __shfl_xor_sync(0xffffffffu, lo3[a], o));
+                hi3[a] = max(hi3[a], __shfl_xor_sync(0xffffffffu, hi3[a], o));
+            }
+            if (lane == 0 && lo3[a] <= hi3[a]) {
+                atomicMin(&s.org_min[a], lo3[a]);
+                atomicMax(&s.org_max[a], hi3[a]);
+            }
+        }
 
         // start bin of every pixel of the group (alternative.cpp:724-727, quirk Q11)
         const int start = flat_bin(d, bx, ty, group);
-
-        // Integer bounds of the group's ray origins (alternative.cpp:720-722), for the shaft cull:
-        // x = pixel column; z / 40 == group with C truncation; y = (H - row) - z (quirk Q11).
-        float org_lo[3], org_hi[3];
-        bool can_cull;
-        {
-            const int zl = group > 0 ? group * kBin : group * kBin - (kBin - 1);
-            const int zh = group >= 0 ? group * kBin + (kBin - 1) : group * kBin;
-            const int wl = d.H - (ty * kBin + kBin - 1), wh = d.H - ty * kBin;
-            const int yl = wl - zh, yh = wh - zl;
-            org_lo[0] = (float)(bx * kBin);
-            org_hi[0] = (float)(bx * kBin + kBin - 1);
-            org_lo[1] = (float)yl;
-            org_hi[1] = (float)yh;
-            org_lo[2] = (float)zl;
-            org_hi[2] = (float)zh;
-            // the origin is cast to short in the reference: only cull when nothing can wrap
-            can_cull = zl >= -32768 && zh <= 32767 && yl >= -32768 && yh <= 32767 && !(p.debug_flags & 1);
-        }
 
         // ---- rounds over (light, step range) segments ----
         int l_cur = 0, ka_cur = 0;  // next unprocessed step of light l_cur
@@ -467,6 +478,27 @@ k_shade(const __grid_constant__ ShadeParams p) {
             // counts and expands them into (bin, slot) pairs with shuffles, so that the dependent
             // loads (entity id -> box) run with dense lanes: entity -> de-duplicate -> box ->
             // shaft cull -> the segment's part of the box list.
+            // Bounds of the group's ray origins for the shaft cull.  The origin is cast to short in
+            // the reference (alternative.cpp:720-722): only cull when nothing can wrap.
+            float org_lo[3], org_hi[3];
+            bool can_cull = !(p.debug_flags & 1);
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                org_lo[a] = (float)s.org_min[a];
+                org_hi[a] = (float)s.org_max[a];
+                can_cull = can_cull && s.org_min[a] >= -32768 && s.org_max[a] <= 32767;
+            }
+            if (p.debug_flags & 2) {  // A/B switch: analytic (loose) bounds instead of the measured ones
+                const int zl = group > 0 ? group * kBin : group * kBin - (kBin - 1);
+                const int zh = group >= 0 ? group * kBin + (kBin - 1) : group * kBin;
+                const int wl = d.H - (ty * kBin + kBin - 1), wh = d.H - ty * kBin;
+                org_lo[0] = (float)(bx * kBin);
+                org_hi[0] = (float)(bx * kBin + kBin - 1);
+                org_lo[1] = (float)(wl - zh);
+                org_hi[1] = (float)(wh - zl);
+                org_lo[2] = (float)zl;
+                org_hi[2] = (float)zh;
+            }
             for (int ob = tid - lane; ob < n_occ; ob += kThreads) {
                 const unsigned mine = ob + lane < n_occ ? s.occ[ob + lane] : 0u;
                 const int my_c = (int)(mine >> 28) < n_fit ? (mine >> 25) & 7 : 0;
