@@ -332,7 +332,7 @@ def ours(args):
         "e2e": {"value": round(e2e, 1), "unit": "Mrays/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "frames_per_s": round(1e3 * args.steps / ms_e2e, 2),
                 "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4)},
-        "gpu_launches": ((10 if world == 1 else 11) * args.steps) * world,
+        "gpu_launches": ((4 if world == 1 else 5) * args.steps) * world,
         "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
                        "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},
         "roofline": roofline, "clocks": clocks,
