@@ -77,7 +77,7 @@ static int fail(int code, const char* fmt, const char* a = "", const char* b = "
                         "%s: %s", #call, cudaGetErrorString(e_));                        \
     } while (0)
 
-constexpr int kMaxChunks = 4;  // row chunks of the pipelined readback in par_render
+constexpr int kMaxChunks = 8;  // row chunks of the pipelined readback in par_render
 
 struct par_ctx {
     par_config cfg;
@@ -116,6 +116,7 @@ struct par_ctx {
     int launches_build = 0, launches_frame = 0, last_n_lights = 0;
     float ambient = 0.25f;
     float last_kernel_ms = 0.f;  // primary + shade of the previous par_render (pipelining heuristic)
+    int readback_chunks = 3;  // row chunks of the pipelined readback (PAR_READBACK_CHUNKS overrides)
     int debug_flags = 0;  // from the PAR_DEBUG_FLAGS environment variable (developer A/B switches)
 };
 
@@ -199,6 +200,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
     c->cfg = *cfg;
     c->ambient = cfg->ambient == 0.f ? 0.25f : cfg->ambient;
     if (const char* e = getenv("PAR_DEBUG_FLAGS")) c->debug_flags = atoi(e);
+    if (const char* e = getenv("PAR_READBACK_CHUNKS")) c->readback_chunks = atoi(e) < 1 ? 1 : atoi(e) > kMaxChunks ? kMaxChunks : atoi(e);
     ViewDims& d = c->d;
     d.W = cfg->width;
     d.H = cfg->height;
@@ -459,7 +461,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
 
     const int tile0 = d.row0 / kBin, tile1 = (d.row1 + kBin - 1) / kBin;
     int n_chunks = 1;
-    if (host_out && d.stripe_n == 1 && tile1 - tile0 >= 4 * kMaxChunks) {  // >= 640 rows
+    if (host_out && d.stripe_n == 1 && tile1 - tile0 >= 4 * c->readback_chunks) {
         // Pipelining costs kernel efficiency (partial waves per chunk), so it is used only when
         // the readback is not small next to the kernels (measured on the previous frame) and
         // the destination is page-locked (a pageable copy would block the launching thread).
@@ -467,7 +469,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
         const bool pinned = cudaPointerGetAttributes(&attr, host_out) == cudaSuccess && attr.type == cudaMemoryTypeHost;
         cudaGetLastError();
         const float copy_ms = (float)(d.row1 - d.row0) * d.W * 4.f / 50e6f;  // ~50 GB/s PCIe gen5
-        if (pinned && c->last_kernel_ms > 0.f && c->last_kernel_ms < 2.5f * copy_ms) n_chunks = kMaxChunks;
+        if (pinned && c->last_kernel_ms > 0.f && c->last_kernel_ms < 2.5f * copy_ms) n_chunks = c->readback_chunks;
     }
     PAR_CUDA(cudaEventRecord(c->ev_f0, c->stream));
     for (int k = 0; k < n_chunks; k++) {
