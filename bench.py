@@ -315,6 +315,11 @@ def ours(args):
                                  "/ CUDA-event time of k_shade; >1 means the kernel legally skips work the reference "
                                  "does (shared grid walks, de-duplicated probes, Q19); see profiles/ for ncu pipe "
                                  "utilisation"})
+    traffic = (load_json(os.path.join(ROOT, "profiles", "roofline_traffic.json"), {}) or {}).get(args.workload, {}).get("k_shade")
+    if traffic and world == 1:
+        roofline["traffic"] = traffic["dram_bytes_read"] + traffic["dram_bytes_write"]
+        roofline["traffic_source"] = traffic["source"] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+        roofline["ncu_issue_active_pct"] = traffic.get("smsp_issue_active_pct")
     hbm_bytes = 16.0 * W * my_rows + 4.0 * W * my_rows
     roofline["hbm"] = {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": round(hbm_bytes / (shade * 1e-3) / 1e9, 1),
                        "peak_gbs": peaks.get("hbm_gbs"), "note": "G-buffer read + RGBA8 write; not the bound"}
