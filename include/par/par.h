@@ -105,9 +105,9 @@ typedef struct par_stats {
     int32_t n_survivors;   /* entities that passed the cull (alternative.cpp:212-219) */
     int32_t n_inserts;     /* (entity, bin) insertions (alternative.cpp:243-267)       */
     uint64_t rays;         /* reference-equivalent rays: rows*W*(1+n_lights)           */
-    uint64_t slab_tests;   /* slab tests actually executed on the device (0 unless the
-                              library was built with PAR_COUNTERS)                      */
-    int32_t reserved[4];
+    uint64_t slab_tests;   /* reserved (0)                                              */
+    float ms_walks;        /* shadow-walk kernel (one warp per tile x z-group x light)  */
+    int32_t reserved[3];
 } par_stats;
 
 typedef struct par_ctx par_ctx;

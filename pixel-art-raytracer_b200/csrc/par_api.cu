@@ -85,7 +85,7 @@ struct par_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_stream = nullptr;  // D2H of finished row chunks, overlapping the next chunk
     cudaEvent_t ev_build0 = nullptr, ev_build1 = nullptr, ev_f0 = nullptr, ev_f2 = nullptr, ev_copy = nullptr;
-    cudaEvent_t ev_chunk[kMaxChunks][3] = {};
+    cudaEvent_t ev_chunk[kMaxChunks][4] = {};  // before primary / after primary / after walks / after shade
     int n_chunks = 1;
     // scene
     int4* d_raw = nullptr;
@@ -106,6 +106,14 @@ struct par_ctx {
     unsigned char* d_atlas_color = nullptr;
     uchar4* d_palette = nullptr;
     int n_sprites = 0, n_palette = 0;
+    // shadow-walk work descriptors and results (primary -> walks -> shade)
+    int* d_tile_ngroups = nullptr;
+    GroupMeta* d_groups = nullptr;
+    int2* d_table = nullptr;
+    int table_lights = 0;  // lights the table is sized for
+    int4* d_pool = nullptr;
+    int pool_cap = 0;
+    int* d_pool_cursor = nullptr;
     // frame
     int4* d_gbuf = nullptr;
     uchar4* d_frame = nullptr;
@@ -233,6 +241,10 @@ int par_create(par_ctx** out, const par_config* cfg) {
         PAR_CUDA(cudaMalloc(&c->d_ctr, sizeof(LoaderCounters)));
         PAR_CUDA(cudaMallocHost(&c->h_ctr, sizeof(LoaderCounters)));
         memset(c->h_ctr, 0, sizeof(LoaderCounters));
+        const size_t tiles = (size_t)d.HW * d.HH;
+        PAR_CUDA(cudaMalloc(&c->d_tile_ngroups, sizeof(int) * tiles));
+        PAR_CUDA(cudaMalloc(&c->d_groups, sizeof(GroupMeta) * tiles * kMaxGroups));
+        PAR_CUDA(cudaMalloc(&c->d_pool_cursor, sizeof(int)));
         PAR_CUDA(cudaMalloc(&c->d_gbuf, sizeof(int4) * px));
         PAR_CUDA(cudaMalloc(&c->d_frame, sizeof(uchar4) * px));
         PAR_CUDA(cudaMemsetAsync(c->d_frame, 0, sizeof(uchar4) * px, c->stream));
@@ -266,6 +278,11 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_atlas_normal);
     cudaFree(c->d_atlas_color);
     cudaFree(c->d_palette);
+    cudaFree(c->d_tile_ngroups);
+    cudaFree(c->d_groups);
+    cudaFree(c->d_table);
+    cudaFree(c->d_pool);
+    cudaFree(c->d_pool_cursor);
     cudaFree(c->d_gbuf);
     cudaFree(c->d_frame);
     cudaFree(c->d_expanded);
@@ -439,6 +456,46 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     pp.atlas_depth = c->d_atlas_depth;
     pp.n_sprites = c->n_sprites;
     pp.gbuf = c->d_gbuf;
+    // Shadow walks run as their own kernel between primary and shade (walks.cu); size its table
+    // for this light count and its pool for ~128 kept boxes per (tile, light).
+    const bool use_walks = n_lights > 0 && !(c->debug_flags & 4);
+    if (use_walks) {
+        const size_t tiles = (size_t)d.HW * d.HH;
+        if (n_lights > c->table_lights) {
+            PAR_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_table);
+            c->d_table = nullptr;
+            c->table_lights = 0;
+            PAR_CUDA(cudaMalloc(&c->d_table, sizeof(int2) * tiles * kMaxGroups * n_lights));
+            c->table_lights = n_lights;
+        }
+        const size_t want = tiles * (size_t)n_lights * 128;
+        const int cap = (int)(want < (1u << 20) ? (1u << 20) : want > 0x7fffffffu / 2 ? 0x7fffffffu / 2 : want);
+        if (cap > c->pool_cap) {
+            PAR_CUDA(cudaStreamSynchronize(c->stream));
+            cudaFree(c->d_pool);
+            c->d_pool = nullptr;
+            c->pool_cap = 0;
+            PAR_CUDA(cudaMalloc(&c->d_pool, sizeof(int4) * (size_t)cap));
+            c->pool_cap = cap;
+        }
+        PAR_CUDA(cudaMemsetAsync(c->d_pool_cursor, 0, sizeof(int), c->stream));
+    }
+    pp.tile_ngroups = use_walks ? c->d_tile_ngroups : nullptr;
+    pp.groups = c->d_groups;
+    WalkParams wp;
+    wp.d = d;
+    wp.ids = c->d_ids;
+    wp.occ4 = c->d_occ4;
+    wp.boxes = c->d_boxes;
+    wp.tile_ngroups = c->d_tile_ngroups;
+    wp.groups = c->d_groups;
+    wp.table = c->d_table;
+    wp.pool = c->d_pool;
+    wp.pool_cursor = c->d_pool_cursor;
+    wp.pool_cap = c->pool_cap;
+    wp.n_lights = n_lights;
+    wp.debug_flags = c->debug_flags;
     ShadeParams sp;
     sp.d = d;
     sp.cnt = c->d_cnt;
@@ -454,10 +511,14 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     sp.ambient = c->ambient;
     sp.phase_cycles = c->d_phase_cycles;  // NULL unless par_debug_phase_timing enabled it
     sp.debug_flags = c->debug_flags;
+    sp.tile_ngroups = use_walks ? c->d_tile_ngroups : nullptr;
+    sp.table = use_walks ? c->d_table : nullptr;
+    sp.pool = c->d_pool;
     sp.out_stripe_T = striped_out ? (d.HH + d.stripe_n - 1) / d.stripe_n : 0;
     memset(sp.lights, 0, sizeof sp.lights);
     for (int l = 0; l < n_lights; l++)
         sp.lights[l] = make_short4(lights[l].x, lights[l].y, lights[l].z, lights[l].radius);
+    memcpy(wp.lights, sp.lights, sizeof wp.lights);
 
     const int tile0 = d.row0 / kBin, tile1 = (d.row1 + kBin - 1) / kBin;
     int n_chunks = 1;
@@ -475,20 +536,22 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     for (int k = 0; k < n_chunks; k++) {
         const int ta = tile0 + (tile1 - tile0) * k / n_chunks, tb = tile0 + (tile1 - tile0) * (k + 1) / n_chunks;
         const int ra = ta * kBin > d.row0 ? ta * kBin : d.row0, rb = tb * kBin < d.row1 ? tb * kBin : d.row1;
-        pp.d.row0 = sp.d.row0 = ra;
-        pp.d.row1 = sp.d.row1 = rb;
+        pp.d.row0 = sp.d.row0 = wp.d.row0 = ra;
+        pp.d.row1 = sp.d.row1 = wp.d.row1 = rb;
         int first_owned, n_owned;
         owned_tile_rows(pp.d, first_owned, n_owned);
-        pp.tile_row_first = sp.tile_row_first = first_owned;
+        pp.tile_row_first = sp.tile_row_first = wp.tile_row_first = first_owned;
         PAR_CUDA(cudaEventRecord(c->ev_chunk[k][0], c->stream));
         PAR_CUDA(launch_primary(pp, c->stream));
         PAR_CUDA(cudaEventRecord(c->ev_chunk[k][1], c->stream));
-        PAR_CUDA(launch_shade(sp, c->stream));
+        if (use_walks) PAR_CUDA(launch_walks(wp, c->stream));
         PAR_CUDA(cudaEventRecord(c->ev_chunk[k][2], c->stream));
+        PAR_CUDA(launch_shade(sp, c->stream));
+        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][3], c->stream));
         if (host_out && d.stripe_n == 1) {
             const size_t first = (size_t)ra * d.W, count = (size_t)(rb - ra) * d.W;
             cudaStream_t cs = n_chunks > 1 ? c->copy_stream : c->stream;
-            if (n_chunks > 1) PAR_CUDA(cudaStreamWaitEvent(cs, c->ev_chunk[k][2], 0));
+            if (n_chunks > 1) PAR_CUDA(cudaStreamWaitEvent(cs, c->ev_chunk[k][3], 0));
             PAR_CUDA(cudaMemcpyAsync(host_out + first, d_out + first, sizeof(par_color) * count,
                                      cudaMemcpyDeviceToHost, cs));
         } else if (host_out) {  // only the owned stripes, each clipped to the band
@@ -506,7 +569,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
         PAR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     }
     c->n_chunks = n_chunks;
-    c->launches_frame = 2 * n_chunks;
+    c->launches_frame = (use_walks ? 3 : 2) * n_chunks;
     c->last_n_lights = n_lights;
     c->frame_valid = true;
     c->frame_timed = true;
@@ -572,10 +635,12 @@ int par_get_stats(par_ctx* c, par_stats* st) {
     if (c->build_timed) PAR_CUDA(cudaEventElapsedTime(&st->ms_grid_build, c->ev_build0, c->ev_build1));
     if (c->frame_timed) {
         for (int k = 0; k < c->n_chunks; k++) {
-            float a = 0.f, b = 0.f;
+            float a = 0.f, w = 0.f, b = 0.f;
             PAR_CUDA(cudaEventElapsedTime(&a, c->ev_chunk[k][0], c->ev_chunk[k][1]));
-            PAR_CUDA(cudaEventElapsedTime(&b, c->ev_chunk[k][1], c->ev_chunk[k][2]));
+            PAR_CUDA(cudaEventElapsedTime(&w, c->ev_chunk[k][1], c->ev_chunk[k][2]));
+            PAR_CUDA(cudaEventElapsedTime(&b, c->ev_chunk[k][2], c->ev_chunk[k][3]));
             st->ms_primary += a;
+            st->ms_walks += w;
             st->ms_shade += b;
         }
         PAR_CUDA(cudaEventElapsedTime(&st->ms_total, c->ev_f0, c->ev_f2));

@@ -17,6 +17,15 @@ cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, i
                                 unsigned* occ4, int* survivors, LoaderCounters* ctr,
                                 cudaStream_t s, int* launches);
 
+// ---- per-tile shadow-walk work descriptors (primary -> walks -> shade) ----
+constexpr int kMaxGroups = 24;    // z-groups per tile with precomputed walks (more: shade walks itself)
+constexpr int kWalkListCap = 64;  // boxes kept per (tile, group, light) list in the pool
+struct GroupMeta {                // one z-group of a tile: all its pixels start their shadow walk in
+    int z;                        //   bin (tile x, tile y, z)  (alternative.cpp:724-727, quirk Q11)
+    int npix;
+    int omin[3], omax[3];         // integer bounds of the group's ray origins (alternative.cpp:720-722)
+};
+
 // ---- primary rays (alternative.cpp:271-383) ----
 struct PrimaryParams {
     ViewDims d;
@@ -27,10 +36,31 @@ struct PrimaryParams {
     int n_sprites;
     int4* gbuf;
     int tile_row_first;  // first owned tile row (bin_y); the next ones are stripe_n apart
+    int* tile_ngroups;   // [HW*HH]: z-groups of the tile (ascending z), -1 = more than kMaxGroups
+    GroupMeta* groups;   // [HW*HH][kMaxGroups]
 };
 size_t primary_smem_bytes(const ViewDims& d, int n_sprites);
 cudaError_t configure_primary(size_t smem);  // per device, before the first launch
 cudaError_t launch_primary(const PrimaryParams& p, cudaStream_t s);
+
+// ---- shadow walks (alternative.cpp:399-476 minus the slab tests): one warp per (tile, group, light) ----
+struct WalkParams {
+    ViewDims d;
+    const int* ids;
+    const unsigned* occ4;
+    const int4* boxes;
+    const int* tile_ngroups;
+    const GroupMeta* groups;
+    int2* table;       // [HW*HH][kMaxGroups][n_lights]: (pool offset, box count) or count -1 = not available
+    int4* pool;        // kept boxes: .x.y.z = the packed 16-bit box record, .w = entity index
+    int* pool_cursor;
+    int pool_cap;
+    int n_lights;
+    int tile_row_first;
+    int debug_flags;
+    short4 lights[64];
+};
+cudaError_t launch_walks(const WalkParams& p, cudaStream_t s);
 
 // ---- shading + shadow rays + RGBA8 pack (alternative.cpp:702-760, 399-500, 40-83) ----
 constexpr int kMaxLights = 64;
@@ -49,7 +79,10 @@ struct ShadeParams {
     float ambient;
     int tile_row_first;
     int out_stripe_T;  // 0: raster output; T > 0: stripe-major staging, T stripes per rank
-    int debug_flags;   // bit 0: disable the shaft cull (A/B measurements only)
+    int debug_flags;   // bit 0: disable the shaft cull, bit 2: ignore precomputed walks (A/B measurements only)
+    const int* tile_ngroups;  // precomputed walks (walks.cu); NULL = shade walks itself
+    const int2* table;
+    const int4* pool;
     unsigned long long* phase_cycles;  // optional debug instrumentation: 16 counters (NULL in production)
     short4 lights[kMaxLights];         // x, y, z, radius (alternative.cpp:619-622)
 };

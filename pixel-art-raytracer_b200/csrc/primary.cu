@@ -17,6 +17,7 @@
 
 namespace par {
 
+constexpr int kNoGroupZ = 0x7fffffff;
 constexpr int kStagedSprites = 4;  // depth tables staged in shared memory when the atlas is this small
 
 // Dynamic shared memory layout: int s_cnt[HL], int s_off[HL+1], int4 A[n], int4 B[n], int2 C[n]
@@ -83,7 +84,10 @@ k_primary(PrimaryParams p) {
     const int col = tid % kBin, rsub = tid / kBin;
     const int i = bx * kBin + col;
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
-#pragma unroll 1
+    int gz[kTileRowsPerThread], oy[kTileRowsPerThread], oz[kTileRowsPerThread];  // for step 3
+#pragma unroll
+    for (int m = 0; m < kTileRowsPerThread; m++) gz[m] = kNoGroupZ;
+#pragma unroll
     for (int m = 0; m < kTileRowsPerThread; m++) {
         const int j = ty * kBin + rsub + 8 * m;
         if (j < ra || j >= rb) continue;
@@ -116,7 +120,88 @@ k_primary(PrimaryParams p) {
             }
         }
         p.gbuf[(size_t)j * d.W + i] = out;
+        if (out.w >= 0) {
+            gz[m] = out.z / kBin;  // ray_bin_z, alternative.cpp:727 (C division truncates toward zero)
+            oy[m] = out.y;
+            oz[m] = out.z;
+        }
     }
+
+    // 3. the tile's z-groups (ascending), their pixel counts and the integer bounds of their ray
+    //    origins: the work descriptors of the shadow-walk kernel (walks.cu).
+    if (!p.tile_ngroups) return;
+    __shared__ int s_group, s_npix, s_min[3], s_max[3];
+    const int tile = ty * d.HW + bx;
+    const int lane = tid & 31;
+    int last = -0x7fffffff - 1, n_groups = 0;
+    for (;;) {
+        if (tid == 0) {
+            s_group = kNoGroupZ;
+            s_npix = 0;
+            s_min[0] = s_min[1] = s_min[2] = 0x7fffffff;
+            s_max[0] = s_max[1] = s_max[2] = -0x7fffffff - 1;
+        }
+        __syncthreads();
+        int mine = kNoGroupZ;
+#pragma unroll
+        for (int m = 0; m < kTileRowsPerThread; m++)
+            if (gz[m] > last) mine = min(mine, gz[m]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+        if (lane == 0 && mine != kNoGroupZ) atomicMin(&s_group, mine);
+        __syncthreads();
+        const int group = s_group;
+        if (group == kNoGroupZ) break;
+        last = group;
+        if (n_groups == kMaxGroups) {  // too many groups: the shade kernel walks this tile itself
+            n_groups = -1;
+            break;
+        }
+        int cnt = 0, lo3[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi3[3] = {-0x7fffffff - 1, -0x7fffffff - 1, -0x7fffffff - 1};
+#pragma unroll
+        for (int m = 0; m < kTileRowsPerThread; m++)
+            if (gz[m] == group) {
+                cnt++;
+                const int o3[3] = {i, oy[m], oz[m]};
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    lo3[a] = min(lo3[a], o3[a]);
+                    hi3[a] = max(hi3[a], o3[a]);
+                }
+            }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                lo3[a] = min(lo3[a], __shfl_xor_sync(0xffffffffu, lo3[a], o));
+                hi3[a] = max(hi3[a], __shfl_xor_sync(0xffffffffu, hi3[a], o));
+            }
+        }
+        if (lane == 0 && cnt) {
+            atomicAdd(&s_npix, cnt);
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                atomicMin(&s_min[a], lo3[a]);
+                atomicMax(&s_max[a], hi3[a]);
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            GroupMeta g;
+            g.z = group;
+            g.npix = s_npix;
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                g.omin[a] = s_min[a];
+                g.omax[a] = s_max[a];
+            }
+            p.groups[(size_t)tile * kMaxGroups + n_groups] = g;
+        }
+        n_groups++;
+    }
+    if (tid == 0) p.tile_ngroups[tile] = n_groups;
 }
 
 size_t primary_smem_bytes(const ViewDims& d, int n_sprites) {

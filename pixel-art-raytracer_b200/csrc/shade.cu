@@ -29,6 +29,7 @@
 //  * Finished RGBA8 pixels are staged in shared memory and leave as 16-byte stores.
 // All fp32 arithmetic is IEEE round-to-nearest with no FMA contraction (-fmad=false).
 #include "par_kernels.cuh"
+#include "shaft.cuh"
 
 namespace par {
 
@@ -147,33 +148,6 @@ __device__ __forceinline__ bool any_box_hit(const float4* __restrict__ boxes, in
     return false;
 }
 
-// Exact-output "shaft" cull of a candidate box for a whole pixel group: all ray origins of the
-// group lie in the integer box [ol, oh] (per axis), all rays go through the light L.  In real
-// arithmetic a pixel's line hits the box iff the per-axis parameter intervals
-// [min, max]{(lo_a - o_a)/(L_a - o_a), (hi_a - o_a)/(L_a - o_a)} intersect (the reference's
-// slab test up to the positive scale |L - o|_1).  Each endpoint is monotonic in o_a, so its hull
-// over the group is attained at the interval ends; if the hulls of the three axes do not
-// intersect — with a 1e-4 relative margin, three orders of magnitude above the fp32 error of
-// the reference's formula — no pixel of the group can pass the reference's test and the box is
-// dropped.  Axes on which some pixel may have a zero direction component (0 in [L-oh, L-ol])
-// impose no constraint, which also covers every NaN/inf case (quirk Q13) conservatively.
-__device__ __forceinline__ bool shaft_may_hit(const float lo[3], const float hi[3], const float L[3],
-                                              const float ol[3], const float oh[3]) {
-    float smin = -INFINITY, smax = INFINITY;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-        const float dl = L[a] - oh[a], dh = L[a] - ol[a];
-        if (dl <= 0.f && dh >= 0.f) continue;
-        // approximate reciprocals (2 ulp) are plenty under the 1e-4 margin
-        const float rl = __fdividef(1.f, dl), rh = __fdividef(1.f, dh);
-        const float v0 = (lo[a] - ol[a]) * rh, v1 = (lo[a] - oh[a]) * rl;
-        const float v2 = (hi[a] - ol[a]) * rh, v3 = (hi[a] - oh[a]) * rl;
-        smin = fmaxf(smin, fminf(fminf(v0, v1), fminf(v2, v3)));
-        smax = fminf(smax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
-    }
-    return !(smin > smax + 1e-4f * (1.f + fabsf(smin) + fabsf(smax)));
-}
-
 // Block-wide exclusive scan of one int per thread (10 warps); *total gets the sum.
 __device__ __forceinline__ int block_exclusive_scan(int v, ShadeSmem& s) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -251,6 +225,12 @@ k_shade(const __grid_constant__ ShadeParams p) {
         }
     }
 
+    // Precomputed walks (walks.cu) for this tile?  Groups are enumerated in ascending z both here
+    // and in the primary kernel, so the k-th group found below is the k-th GroupMeta.
+    const int tile = ty * d.HW + bx;
+    const bool tile_pre = p.table && !(p.debug_flags & 4) && p.tile_ngroups[tile] >= 0;
+    int group_index = -1;
+
     int last_group = -0x7fffffff - 1;
     for (;;) {
         // ---- next group: the smallest start-bin z not yet processed in this tile ----
@@ -273,6 +253,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
         const int group = s.group;
         if (group == kNoGroup) break;
         last_group = group;
+        group_index++;
 
         // ---- compact the group's pixels into a dense list ----
         int my_n = 0;
@@ -318,9 +299,58 @@ k_shade(const __grid_constant__ ShadeParams p) {
         int nseg_try = kSegMax;
         bool fresh = true;          // first round of the group: acc starts at 0
         while (l_cur < n_lights) {
-            // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
             __syncthreads();  // previous round fully consumed (lists, segments, pix list complete)
             mark(fresh ? kPhCompact : kPhShade);
+            int n_fit = 0;
+            bool fetched = false;
+            if (tile_pre && ka_cur == 0 && kb_try < 0) {
+                // ---- fast path: the walks of this group were done by walks.cu; fetch their box lists ----
+                const int nseg = min(kSegMax, n_lights - l_cur);
+                if (tid < nseg) {
+                    const int2 e = p.table[((size_t)tile * kMaxGroups + group_index) * n_lights + l_cur + tid];
+                    Segment& g = s.seg[tid];
+                    g.light = l_cur + tid;
+                    g.ka = 0;
+                    g.kb = g.steps = 1;  // a whole walk
+                    g.item0 = e.x;       // pool offset
+                    g.count = g.fill = e.y;
+                }
+                __syncthreads();
+                bool all = true;
+                int total = 0;
+                for (int q = 0; q < nseg; q++) {
+                    const int c = s.seg[q].count;
+                    all = all && c >= 0;
+                    if (all && n_fit == q && total + c <= kListCap) {
+                        total += c;
+                        n_fit = q + 1;
+                    }
+                }
+                if (all) {  // (a list is at most kWalkListCap <= kListCap boxes, so n_fit >= 1)
+                    fetched = true;
+                    if (tid < n_fit) {
+                        int base = 0;
+                        for (int q = 0; q < tid; q++) base += s.seg[q].count;
+                        s.seg[tid].base = base;
+                    }
+                    for (int e0 = tid; e0 < total; e0 += kThreads) {
+                        int q = 0, off = e0;
+                        while (off >= s.seg[q].count) off -= s.seg[q++].count;
+                        const int4 rec = p.pool[s.seg[q].item0 + off];
+                        const Box b = unpack_box(rec);
+                        s.list[2 * e0] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(rec.w));
+                        s.list[2 * e0 + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
+                                                         (float)(b.pz + b.ez), 0.f);
+                    }
+                    __syncthreads();
+                    mark(kPhGather);
+                } else {
+                    n_fit = 0;
+                    __syncthreads();  // everyone has read the segment table before it is rewritten
+                }
+            }
+            if (!fetched) {
+            // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
             if (tid < nseg_try && l_cur + tid < n_lights) {
                 const short4 lt = p.lights[l_cur + tid];
                 // light bin, alternative.cpp:729-732 ('/' truncates toward zero)
@@ -444,7 +474,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
             mark(kPhWalk);
             const int n_occ = s.n_occ;  // every occupied bin holds >= 1 box, so n_occ <= sum of counts
             // D. how many leading segments fit the box list?  (every thread, redundantly)
-            int n_fit = 0;
+            n_fit = 0;
             {
                 int total = 0;
                 while (n_fit < nseg && total + s.seg[n_fit].count <= kListCap) {
@@ -563,6 +593,8 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 atomicAdd(&p.phase_cycles[11], kept);
                 atomicAdd(&p.phase_cycles[12], (unsigned long long)npix * n_fit);
             }
+
+            }  // !fetched
 
             // F. phase 3: one lane per pixel of the group
             const bool final_round = s.seg[n_fit - 1].light == n_lights - 1 &&

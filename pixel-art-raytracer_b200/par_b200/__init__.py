@@ -55,7 +55,8 @@ class Stats(C.Structure):
     _fields_ = [("ms_grid_build", C.c_float), ("ms_primary", C.c_float), ("ms_shade", C.c_float),
                 ("ms_total", C.c_float), ("kernel_launches", C.c_int32),
                 ("n_entities", C.c_int32), ("n_survivors", C.c_int32), ("n_inserts", C.c_int32),
-                ("rays", C.c_uint64), ("slab_tests", C.c_uint64), ("reserved", C.c_int32 * 4)]
+                ("rays", C.c_uint64), ("slab_tests", C.c_uint64), ("ms_walks", C.c_float),
+                ("reserved", C.c_int32 * 3)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
