@@ -458,7 +458,10 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     pp.gbuf = c->d_gbuf;
     // Shadow walks run as their own kernel between primary and shade (walks.cu); size its table
     // for this light count and its pool for ~128 kept boxes per (tile, light).
-    const bool use_walks = n_lights > 0 && !(c->debug_flags & 4);
+    // EXPERIMENTAL, off by default (PAR_DEBUG_FLAGS bit 3): the in-kernel walks of k_shade are the
+    // product path; the separate kernel only pays off for many-light scenes once its per-thread
+    // loads are batched.
+    const bool use_walks = n_lights > 0 && (c->debug_flags & 8) && !(c->debug_flags & 4);
     if (use_walks) {
         const size_t tiles = (size_t)d.HW * d.HH;
         if (n_lights > c->table_lights) {

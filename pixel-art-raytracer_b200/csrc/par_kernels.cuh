@@ -19,7 +19,7 @@ cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, i
 
 // ---- per-tile shadow-walk work descriptors (primary -> walks -> shade) ----
 constexpr int kMaxGroups = 24;    // z-groups per tile with precomputed walks (more: shade walks itself)
-constexpr int kWalkListCap = 64;  // boxes kept per (tile, group, light) list in the pool
+constexpr int kWalkListCap = 16;  // boxes kept per (tile, group, light) list in the pool
 struct GroupMeta {                // one z-group of a tile: all its pixels start their shadow walk in
     int z;                        //   bin (tile x, tile y, z)  (alternative.cpp:724-727, quirk Q11)
     int npix;

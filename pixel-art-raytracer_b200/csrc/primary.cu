@@ -22,6 +22,7 @@ constexpr int kStagedSprites = 4;  // depth tables staged in shared memory when 
 
 // Dynamic shared memory layout: int s_cnt[HL], int s_off[HL+1], int4 A[n], int4 B[n], int2 C[n]
 // with n <= 7*HL, then (optionally) the depth tables.
+template <bool kEmitGroups>
 __global__ void __launch_bounds__(kTileThreads)
 k_primary(PrimaryParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -80,47 +81,72 @@ k_primary(PrimaryParams p) {
     __syncthreads();
     const int n = s_off[d.HL];
 
-    // 2. per-pixel walk
+    // 2. per-pixel walk.  A thread owns 5 pixels of ONE screen column (8 rows apart), so the
+    //    x half of the hit test (quirk Q6) is shared by them: the entry list is traversed once per
+    //    thread, and per pixel only (best key, winning entry, its depth, run state) is kept; the
+    //    G-buffer record is rebuilt from the winning entry at the end.
     const int col = tid % kBin, rsub = tid / kBin;
     const int i = bx * kBin + col;
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
-    int gz[kTileRowsPerThread], oy[kTileRowsPerThread], oz[kTileRowsPerThread];  // for step 3
-#pragma unroll
-    for (int m = 0; m < kTileRowsPerThread; m++) gz[m] = kNoGroupZ;
+    int wj[kTileRowsPerThread], best[kTileRowsPerThread], win[kTileRowsPerThread], wdep[kTileRowsPerThread];
+    int run[kTileRowsPerThread];
+    unsigned any_bits = 0, live = 0;  // bit m: has_intersected in the current bin / pixel still marching
 #pragma unroll
     for (int m = 0; m < kTileRowsPerThread; m++) {
         const int j = ty * kBin + rsub + 8 * m;
-        if (j < ra || j >= rb) continue;
-        const int wj = (short)(d.H - j);  // world_j, alternative.cpp:280
-        int best = INT_MIN;               // closest_entity_depth, alternative.cpp:289
-        int run = 0, any = 0;             // intersected_bin_count / has_intersected
-        int4 out = make_int4(0, 0, 0, -1);  // miss: entity 0, y 0, z 0 (quirk Q10)
-        for (int k = 0; k < n; k++) {
-            const int2 c = sC[k];
-            if (c.y & 1) {  // first entry of a bin: close the previous bin (alternative.cpp:368-374)
-                run += any;
-                any = 0;
-                if (run >= 2) break;
-                if (c.y & 2) run = 0;  // an empty bin in between resets the run (alternative.cpp:298-300)
+        wj[m] = (short)(d.H - j);  // world_j, alternative.cpp:280
+        best[m] = INT_MIN;         // closest_entity_depth, alternative.cpp:289
+        win[m] = -1;               // miss (quirk Q10)
+        wdep[m] = 0;
+        run[m] = 0;                // intersected_bin_count
+        if (j >= ra && j < rb) live |= 1u << m;
+    }
+    for (int k = 0; k < n && live; k++) {
+        const int2 c = sC[k];
+        if (c.y & 1) {  // first entry of a bin: close the previous bin (alternative.cpp:368-374)
+#pragma unroll
+            for (int m = 0; m < kTileRowsPerThread; m++) {
+                run[m] += (any_bits >> m) & 1;
+                if (run[m] >= 2) live &= ~(1u << m);  // two adjacent hit bins end the march (quirk Q9)
+                if (c.y & 2) run[m] = 0;              // an empty bin in between resets the run (298-300)
             }
-            const int4 a = sA[k];
-            if (i >= a.x && i < a.y && wj > a.z && wj <= a.w) {  // quirk Q6
-                const int4 b = sB[k];
-                const int spr = c.y >> 2;
-                const int row = a.w - wj;
-                const int idx = row * kSpriteW + (i - a.x);  // quirk Q7
-                const int dep = staged ? s_depth[spr * kTexels + idx]
-                                       : __ldg(&p.atlas_depth[spr * kTexels + idx]);
-                const int key = b.x + min(0, b.y - row) - dep;  // quirk Q8
-                if (best < key) {  // strict: ties keep the earlier (bin_z, slot)
-                    best = key;
-                    out = make_int4(c.x, b.w - row - dep, b.z + dep, idx | spr << 10);  // Q11
-                    any = 1;
-                }
+            any_bits = 0;
+            if (!live) break;
+        }
+        const int4 a = sA[k];
+        if (i < a.x || i >= a.y) continue;  // x half of quirk Q6, the same for all 5 pixels
+        const int4 b = sB[k];
+        const int spr = c.y >> 2;
+#pragma unroll
+        for (int m = 0; m < kTileRowsPerThread; m++) {
+            if (!((live >> m) & 1) || !(wj[m] > a.z && wj[m] <= a.w)) continue;  // y half of Q6
+            const int row = a.w - wj[m];
+            const int idx = row * kSpriteW + (i - a.x);  // quirk Q7
+            const int dep = staged ? s_depth[spr * kTexels + idx] : __ldg(&p.atlas_depth[spr * kTexels + idx]);
+            const int key = b.x + min(0, b.y - row) - dep;  // quirk Q8
+            if (best[m] < key) {  // strict: ties keep the earlier (bin_z, slot)
+                best[m] = key;
+                win[m] = k;
+                wdep[m] = dep;
+                any_bits |= 1u << m;
             }
         }
+    }
+    int gz[kTileRowsPerThread], oy[kTileRowsPerThread], oz[kTileRowsPerThread];  // for step 3
+#pragma unroll
+    for (int m = 0; m < kTileRowsPerThread; m++) {
+        gz[m] = kNoGroupZ;
+        const int j = ty * kBin + rsub + 8 * m;
+        if (j < ra || j >= rb) continue;
+        int4 out = make_int4(0, 0, 0, -1);  // miss: entity 0, y 0, z 0 (quirk Q10)
+        if (win[m] >= 0) {
+            const int4 a = sA[win[m]], b = sB[win[m]];
+            const int2 c = sC[win[m]];
+            const int row = a.w - wj[m], idx = row * kSpriteW + (i - a.x);
+            out = make_int4(c.x, b.w - row - wdep[m], b.z + wdep[m], idx | (c.y >> 2) << 10);  // Q11
+        }
         p.gbuf[(size_t)j * d.W + i] = out;
-        if (out.w >= 0) {
+        if (kEmitGroups && out.w >= 0) {
             gz[m] = out.z / kBin;  // ray_bin_z, alternative.cpp:727 (C division truncates toward zero)
             oy[m] = out.y;
             oz[m] = out.z;
@@ -129,7 +155,7 @@ k_primary(PrimaryParams p) {
 
     // 3. the tile's z-groups (ascending), their pixel counts and the integer bounds of their ray
     //    origins: the work descriptors of the shadow-walk kernel (walks.cu).
-    if (!p.tile_ngroups) return;
+    if (!kEmitGroups) return;
     __shared__ int s_group, s_npix, s_min[3], s_max[3];
     const int tile = ty * d.HW + bx;
     const int lane = tid & 31;
@@ -213,7 +239,9 @@ size_t primary_smem_bytes(const ViewDims& d, int n_sprites) {
 
 cudaError_t configure_primary(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(k_primary, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_primary<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e) return e;
+    return cudaFuncSetAttribute(k_primary<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 
 cudaError_t launch_primary(const PrimaryParams& p, cudaStream_t s) {
@@ -222,7 +250,10 @@ cudaError_t launch_primary(const PrimaryParams& p, cudaStream_t s) {
     owned_tile_rows(d, first, tile_rows);
     if (tile_rows <= 0) return cudaSuccess;
     size_t smem = primary_smem_bytes(d, p.n_sprites);
-    k_primary<<<tile_rows * d.HW, kTileThreads, smem, s>>>(p);
+    if (p.tile_ngroups)
+        k_primary<true><<<tile_rows * d.HW, kTileThreads, smem, s>>>(p);
+    else
+        k_primary<false><<<tile_rows * d.HW, kTileThreads, smem, s>>>(p);
     return cudaGetLastError();
 }
 
