@@ -62,3 +62,16 @@ def test_headless_driver_prints_reference_hashes(par, golden):
     out = subprocess.run([exe, "--frames", "40", "--script", "C"], check=True, capture_output=True, text=True).stdout
     got = [ln.split()[1] for ln in out.splitlines()]
     assert got == golden["tier0_480x320x320_scriptC_240"]["fnv1a64"][:40]
+
+
+def test_headless_driver_full_c4_sequence(par, golden):
+    """Config 4 end to end in C++: all 240 frames of key script D at 1920x1080 (per-frame scene
+    upload + render + overlay); the printed hash file must have the sha256 of the one the real
+    reference produced."""
+    import hashlib
+    exe = os.path.join(PKG, "build", "par_headless")
+    if not os.path.exists(exe):
+        pytest.skip("par_headless not built")
+    out = subprocess.run([exe, "--view", "1920", "1080", "1080", "--frames", "240", "--script", "D"],
+                         check=True, capture_output=True).stdout
+    assert hashlib.sha256(out).hexdigest() == golden["tier1_1920x1080x1080_scriptD_240"]["hash_file_sha256"]

@@ -37,11 +37,51 @@ def run(name, W, H, L, boxes, lights, reps=5):
         print(json.dumps(best), flush=True)
 
 
+def run_sequence(W=1920, H=1080, L=1080, frames=240):
+    """Config 4: the 240-frame key script D (player + light move): per frame a scene upload
+    (par_set_scene from pinned memory) and a render with the frame read back (pinned)."""
+    def script_c_key(f):
+        k = f - 1
+        if k < 0:
+            return None
+        for n, key in ((30, "R"), (20, "U"), (50, "L"), (30, "D"), (30, "P"), (40, "R"), (30, "p"), (9, "U")):
+            if k < n:
+                return key
+            k -= n
+        return None
+    boxes = par.pinned_empty(len(par.scene_default()), par.AABB)
+    boxes[:] = par.scene_default()
+    lights = par.light_default()
+    out = par.pinned_empty((H, W), par.COLOR)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        for rep in range(2):  # first pass warms up
+            boxes[:] = par.scene_default()
+            lights = par.light_default()
+            t0 = time.perf_counter()
+            gpu = 0.0
+            for f in range(frames):
+                k = script_c_key(f)
+                if k:
+                    par.apply_key(k, boxes, lights)
+                if f >= 1:
+                    par.apply_key("o", boxes, lights)
+                r.set_scene(boxes)
+                _, st = r.render(lights, out=out)
+                gpu += st["ms_grid_build"] + st["ms_total"]
+            dt = time.perf_counter() - t0
+        print(json.dumps({"config": f"C4 240-frame script D {W}x{H}, upload + render + readback per frame",
+                          "frames_per_s": round(frames / dt, 1), "ms_per_frame_wall": round(dt / frames * 1e3, 3),
+                          "ms_per_frame_gpu_kernels": round(gpu / frames, 3)}), flush=True)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c1", "c4", "c2", "c3", "c5"]
     d, l = par.scene_default(), par.light_default()
     if "c1" in which:
         run("C1 default 480x320", 480, 320, 320, d, l)
+    if "c4seq" in which:
+        run_sequence()
     if "c4" in which:
         run("C4 default 1920x1080 frame0", 1920, 1080, 1080, d, l)
     if "c2" in which:
