@@ -66,7 +66,8 @@ struct Segment {
     int count;         // boxes found (before de-duplication)
     int base;          // first slot of the segment in the box list
     int fill;          // boxes stored (after de-duplication)
-    int pad;
+    int octant;        // >= 0: every ray of the group has this sign octant (bit a = component a negative) and
+                       // the boxes are stored as (near, far) corners; -1: mixed, boxes stored as (lo, hi)
 };
 
 struct ShadeSmem {
@@ -115,34 +116,32 @@ __device__ __forceinline__ bool slab_hit_fast(const float4 lo, const float4 hi, 
     return tmax >= tmin;
 }
 
-// Same test again when, in addition, the signs of the three inverse-direction components are
-// known (octant bit a set = component a negative).  With lo <= hi, subtraction and a
-// multiplication by a constant are monotonic in fp32, so min(x1,x2) IS the product of the
-// near corner (lo for a positive component, hi for a negative one) and max(x1,x2) that of
-// the far corner: the six inner min/max disappear.
-template <int kOctant>
-__device__ __forceinline__ bool slab_hit_octant(const float4 lo, const float4 hi, float ox, float oy,
-                                                float oz, float ix, float iy, float iz) {
-    const float nx = ((kOctant & 1) ? hi.x : lo.x) - ox, fx = ((kOctant & 1) ? lo.x : hi.x) - ox;
-    const float ny = ((kOctant & 2) ? hi.y : lo.y) - oy, fy = ((kOctant & 2) ? lo.y : hi.y) - oy;
-    const float nz = ((kOctant & 4) ? hi.z : lo.z) - oz, fz = ((kOctant & 4) ? lo.z : hi.z) - oz;
-    const float tmin = fmaxf(fmaxf(nx * ix, ny * iy), nz * iz);
-    const float tmax = fminf(fminf(fx * ix, fy * iy), fz * iz);
+// Same test again when, in addition, the signs of the three inverse-direction components are the
+// same for every pixel of the group (the light lies strictly outside the group's origin bounds
+// on every axis).  With lo <= hi, subtraction and a multiplication by a constant are monotonic in
+// fp32, so min(x1,x2) IS the product of the near corner (lo for a positive component, hi for a
+// negative one) and max(x1,x2) that of the far corner: the six inner min/max disappear.  The
+// gather stores the box as (near, far) corners for such a segment, so one code path serves all
+// eight sign octants: 6 FADD + 6 FMUL + 2 FMNMX3 per box.
+__device__ __forceinline__ bool slab_hit_near_far(const float4 nr, const float4 fr, float ox, float oy,
+                                                  float oz, float ix, float iy, float iz) {
+    const float tmin = fmaxf(fmaxf((nr.x - ox) * ix, (nr.y - oy) * iy), (nr.z - oz) * iz);
+    const float tmax = fminf(fminf((fr.x - ox) * ix, (fr.y - oy) * iy), (fr.z - oz) * iz);
     return tmax >= tmin;
 }
 
-// kMode 0..7: sign octant known for the whole warp; 8: NaN-free, mixed signs; 9: exact.
+// kMode 0: (near, far) storage, sign octant uniform; 1: NaN-free, (lo, hi) storage; 2: exact.
 template <int kMode>
 __device__ __forceinline__ bool any_box_hit(const float4* __restrict__ boxes, int n, int self,
                                             float ox, float oy, float oz, float ix, float iy,
                                             float iz) {
-#pragma unroll 2
+#pragma unroll 1
     for (int e = 0; e < n; e++) {
         const float4 lo = boxes[2 * e], hi = boxes[2 * e + 1];
         bool hit;
-        if (kMode == 9) hit = slab_hit_exact(lo, hi, ox, oy, oz, ix, iy, iz);
-        else if (kMode == 8) hit = slab_hit_fast(lo, hi, ox, oy, oz, ix, iy, iz);
-        else hit = slab_hit_octant<kMode & 7>(lo, hi, ox, oy, oz, ix, iy, iz);
+        if (kMode == 2) hit = slab_hit_exact(lo, hi, ox, oy, oz, ix, iy, iz);
+        else if (kMode == 1) hit = slab_hit_fast(lo, hi, ox, oy, oz, ix, iy, iz);
+        else hit = slab_hit_near_far(lo, hi, ox, oy, oz, ix, iy, iz);
         if (hit && __float_as_int(lo.w) != self) return true;  // quirk Q17: own entity never shadows
     }
     return false;
@@ -172,6 +171,30 @@ __device__ __forceinline__ int block_exclusive_scan(int v, ShadeSmem& s) {
     }
     __syncthreads();
     return s.warp_scan[w] + incl - v;
+}
+
+// Box -> shared list slot `at`: (lo, hi) corners, or (near, far) corners for a uniform sign octant.
+__device__ __forceinline__ void store_box(ShadeSmem& s, int at, const Box& b, int ent, int octant) {
+    const float lx = (float)b.px, ly = (float)b.py, lz = (float)b.pz;
+    const float hx = (float)(b.px + b.ex), hy = (float)(b.py + b.ey), hz = (float)(b.pz + b.ez);
+    const bool sx = octant > 0 && (octant & 1), sy = octant > 0 && (octant & 2), sz = octant > 0 && (octant & 4);
+    s.list[2 * at] = make_float4(sx ? hx : lx, sy ? hy : ly, sz ? hz : lz, __int_as_float(ent));
+    s.list[2 * at + 1] = make_float4(sx ? lx : hx, sy ? ly : hy, sz ? lz : hz, 0.f);
+}
+
+// Sign octant shared by every ray of the current group towards light lt, or -1.  Uses the measured
+// integer bounds of the group's origins; strict separation also guarantees that no direction
+// component is zero, i.e. that the NaN cases of quirk Q13 cannot occur for this (group, light).
+__device__ __forceinline__ int group_octant(const ShadeSmem& s, short4 lt) {
+    const int L[3] = {lt.x, lt.y, lt.z};
+    int oct = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (s.org_min[a] < -32768 || s.org_max[a] > 32767) return -1;  // origins are cast to short
+        if (L[a] < s.org_min[a]) oct |= 1 << a;
+        else if (!(L[a] > s.org_max[a])) return -1;
+    }
+    return oct;
 }
 
 __device__ __forceinline__ unsigned quantise(uchar4 c, float f) {  // sprites.hpp:8-16
@@ -314,6 +337,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     g.kb = g.steps = 1;  // a whole walk
                     g.item0 = e.x;       // pool offset
                     g.count = g.fill = e.y;
+                    g.octant = group_octant(s, p.lights[l_cur + tid]);
                 }
                 __syncthreads();
                 bool all = true;
@@ -337,10 +361,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         int q = 0, off = e0;
                         while (off >= s.seg[q].count) off -= s.seg[q++].count;
                         const int4 rec = p.pool[s.seg[q].item0 + off];
-                        const Box b = unpack_box(rec);
-                        s.list[2 * e0] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(rec.w));
-                        s.list[2 * e0 + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
-                                                         (float)(b.pz + b.ez), 0.f);
+                        store_box(s, e0, unpack_box(rec), rec.w, s.seg[q].octant);
                     }
                     __syncthreads();
                     mark(kPhGather);
@@ -368,6 +389,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 g.kb = (tid == 0 && kb_try >= 0) ? kb_try : g.steps;
                 g.count = 0;
                 g.fill = 0;
+                g.octant = group_octant(s, lt);
             }
             for (int i = tid; i < kHashSize; i += kThreads) s.hash[i] = kEmpty;
             __syncthreads();
@@ -576,9 +598,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     int base = 0;
                     for (int r = 0; r < q; r++) base += s.seg[r].count;
                     const int at = base + atomicAdd(&s.seg[q].fill, 1);
-                    s.list[2 * at] = make_float4((float)b.px, (float)b.py, (float)b.pz, __int_as_float(ent));
-                    s.list[2 * at + 1] = make_float4((float)(b.px + b.ex), (float)(b.py + b.ey),
-                                                     (float)(b.pz + b.ez), 0.f);
+                    store_box(s, at, b, ent, s.seg[q].octant);
                 }
             }
             __syncthreads();
@@ -643,28 +663,15 @@ k_shade(const __grid_constant__ ShadeParams p) {
                     // a NaN can only arise from a zero (or NaN) direction component (quirk Q13)
                     const bool nan_free = fabsf(tx) > 0.f && fabsf(tyv) > 0.f && fabsf(tz) > 0.f;
                     const float4* boxes = s.list + 2 * sg.base;
-                    const unsigned testing = __ballot_sync(0xffffffffu, test);
-                    if (testing) {
+                    if (__any_sync(0xffffffffu, test)) {
                         // warp-uniform choice of the slab-test variant
-                        const int octant = (ix < 0.f) | (iy < 0.f) << 1 | (iz < 0.f) << 2;
-                        const int first = __shfl_sync(0xffffffffu, octant, __ffs(testing) - 1);
-                        int mode = first;
-                        if (__any_sync(0xffffffffu, test && octant != first)) mode = 8;
-                        if (__any_sync(0xffffffffu, test && !nan_free)) mode = 9;
                         bool hit = false;
-                        if (test) {
-                            switch (mode) {
-                                case 0: hit = any_box_hit<0>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 1: hit = any_box_hit<1>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 2: hit = any_box_hit<2>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 3: hit = any_box_hit<3>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 4: hit = any_box_hit<4>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 5: hit = any_box_hit<5>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 6: hit = any_box_hit<6>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 7: hit = any_box_hit<7>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                case 8: hit = any_box_hit<8>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                                default: hit = any_box_hit<9>(boxes, n, g.x, ox, oy, oz, ix, iy, iz); break;
-                            }
+                        if (sg.octant >= 0) {
+                            if (test) hit = any_box_hit<0>(boxes, n, g.x, ox, oy, oz, ix, iy, iz);
+                        } else if (!__any_sync(0xffffffffu, test && !nan_free)) {
+                            if (test) hit = any_box_hit<1>(boxes, n, g.x, ox, oy, oz, ix, iy, iz);
+                        } else {
+                            if (test) hit = any_box_hit<2>(boxes, n, g.x, ox, oy, oz, ix, iy, iz);
                         }
                         if (hit) shadowed = true;
                     }
