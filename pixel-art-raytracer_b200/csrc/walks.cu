@@ -16,7 +16,7 @@
 namespace par {
 
 constexpr int kWalkThreads = 128;
-constexpr int kWalkOccCap = 32;  // occupied bins one walk may find before it is left to the shade kernel
+constexpr int kWalkOccCap = 32;  // occupied bins buffered between two gathers of one walk
 
 // Shared memory: per-thread lists, entry-major so that a warp's accesses never conflict.
 struct WalkSmem {
@@ -64,33 +64,6 @@ k_walk(const __grid_constant__ WalkParams p) {
         const float sx = dx / big, sy = dy / big, sz = dz / big;
         const int sxy = d.HH * d.HL;
 
-        // ---- walk: sequential fp32 accumulation from the start bin (quirk Q15) ----
-        float px = (float)bx, py = (float)ty, pz = (float)group;
-        int x0 = bx, y0 = ty, z0 = group;
-        for (int kk = 0; kk < steps; kk++) {
-            px = px + sx;
-            py = py + sy;
-            pz = pz + sz;
-            const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
-            // distinct bins among the step's 7 probes = non-empty subsets of the changed axes (see
-            // shade.cu); start-bin skip Q16, flat-index bounds Q18
-            const int changed = (x1 != x0) | (y1 != y0) << 1 | (z1 != z0) << 2;
-            const int fx0 = x0 * sxy, fx1 = x1 * sxy, fy0 = y0 * d.HL, fy1 = y1 * d.HL;
-            for (int sub = changed; sub; sub = (sub - 1) & changed) {
-                const int f = ((sub & 1) ? fx1 : fx0) + ((sub & 2) ? fy1 : fy0) + ((sub & 4) ? z1 : z0);
-                if (f == start || (unsigned)f >= (unsigned)d.V) continue;
-                const unsigned c = (__ldg(&p.occ4[f >> 3]) >> ((f & 7) * 4)) & 7;
-                if (!c) continue;
-                if (n_occ < kWalkOccCap) s.occ[n_occ][tid] = c << 25 | (unsigned)f;
-                n_occ++;
-            }
-            x0 = x1;
-            y0 = y1;
-            z0 = z1;
-        }
-        overflow = n_occ > kWalkOccCap;
-
-        // ---- gather: entity -> box -> shaft cull -> de-duplicate against the kept list ----
         float org_lo[3], org_hi[3];
         bool can_cull = !(p.debug_flags & 1);
 #pragma unroll
@@ -100,25 +73,54 @@ k_walk(const __grid_constant__ WalkParams p) {
             can_cull = can_cull && gm.omin[a] >= -32768 && gm.omax[a] <= 32767;  // origins are cast to short
         }
         const float lp[3] = {(float)lt.x, (float)lt.y, (float)lt.z};
-        for (int i = 0; i < n_occ && !overflow; i++) {
-            const unsigned desc = s.occ[i][tid];
-            const int c = (desc >> 25) & 7;
-            const int* slot = p.ids + (size_t)(desc & 0x1ffffffu) * kSlots;
-            for (int j = 0; j < c; j++) {
-                const int ent = slot[j];
-                const Box b = unpack_box(p.boxes[ent]);
-                if (can_cull) {
-                    const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
-                    const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
-                    if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
+
+        // ---- walk (sequential fp32 accumulation from the start bin, quirk Q15) in stretches that
+        //      fill the occupied-bin buffer, each followed by a gather of the buffered bins ----
+        float px = (float)bx, py = (float)ty, pz = (float)group;
+        int x0 = bx, y0 = ty, z0 = group;
+        int kk = 0;
+        while (kk < steps && !overflow) {
+            n_occ = 0;
+            for (; kk < steps && n_occ + 7 <= kWalkOccCap; kk++) {
+                px = px + sx;
+                py = py + sy;
+                pz = pz + sz;
+                const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
+                // distinct bins among the step's 7 probes = non-empty subsets of the changed axes
+                // (see shade.cu); start-bin skip Q16, flat-index bounds Q18
+                const int changed = (x1 != x0) | (y1 != y0) << 1 | (z1 != z0) << 2;
+                const int fx0 = x0 * sxy, fx1 = x1 * sxy, fy0 = y0 * d.HL, fy1 = y1 * d.HL;
+                for (int sub = changed; sub; sub = (sub - 1) & changed) {
+                    const int f = ((sub & 1) ? fx1 : fx0) + ((sub & 2) ? fy1 : fy0) + ((sub & 4) ? z1 : z0);
+                    if (f == start || (unsigned)f >= (unsigned)d.V) continue;
+                    const unsigned c = (__ldg(&p.occ4[f >> 3]) >> ((f & 7) * 4)) & 7;
+                    if (c) s.occ[n_occ++][tid] = c << 25 | (unsigned)f;
                 }
-                bool dup = false;
-                for (int q = 0; q < min(n_kept, kWalkListCap); q++) dup = dup || s.kept[q][tid] == ent;
-                if (dup) continue;
-                if (n_kept < kWalkListCap) s.kept[n_kept][tid] = ent;
-                n_kept++;
+                x0 = x1;
+                y0 = y1;
+                z0 = z1;
             }
-            overflow = n_kept > kWalkListCap;
+            // gather: entity -> box -> shaft cull -> de-duplicate against the kept list
+            for (int i = 0; i < n_occ && !overflow; i++) {
+                const unsigned desc = s.occ[i][tid];
+                const int c = (desc >> 25) & 7;
+                const int* slot = p.ids + (size_t)(desc & 0x1ffffffu) * kSlots;
+                for (int j = 0; j < c; j++) {
+                    const int ent = slot[j];
+                    const Box b = unpack_box(p.boxes[ent]);
+                    if (can_cull) {
+                        const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
+                        const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
+                        if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
+                    }
+                    bool dup = false;
+                    for (int q = 0; q < min(n_kept, kWalkListCap); q++) dup = dup || s.kept[q][tid] == ent;
+                    if (dup) continue;
+                    if (n_kept < kWalkListCap) s.kept[n_kept][tid] = ent;
+                    n_kept++;
+                }
+                overflow = n_kept > kWalkListCap;
+            }
         }
     }
 

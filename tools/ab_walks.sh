@@ -1,5 +1,5 @@
-# Developer A/B of the separate walk kernel on one box: flags 0 = walks.cu, 4 = shade walks itself
-for f in ${FLAGS:-0 4}; do echo "== PAR_DEBUG_FLAGS=$f"; PAR_DEBUG_FLAGS=$f timeout 300 python tools/probe_gpu.py ${CFGS:-c2 c3 c5} 2>&1 | python -c "
+# Developer A/B of the separate walk kernel on one box: flags 8 = walks.cu feeds k_shade, 0 = k_shade walks itself
+for f in ${FLAGS:-8 0}; do echo "== PAR_DEBUG_FLAGS=$f"; PAR_DEBUG_FLAGS=$f timeout 300 python tools/probe_gpu.py ${CFGS:-c2 c3 c5} 2>&1 | python -c "
 import sys,json
 for l in sys.stdin:
     try: d=json.loads(l)
