@@ -229,17 +229,20 @@ k_shade(const __grid_constant__ ShadeParams p) {
         }
     };
 
-    // ---- load the tile: start-bin z ("group") of every hit pixel; miss pixels are final ----
-    int gz[kPixPerThread];
+    // ---- load the tile: world z of every hit pixel (its start-bin z, the "group", is z / 40: ray_bin_z,
+    //      alternative.cpp:727, C division truncating toward zero); miss pixels are final ----
+    constexpr int kNoZ = -0x7fffffff - 1;
+    auto group_of = [](int z) { return z == kNoZ ? kNoGroup : z / kBin; };
+    int zv[kPixPerThread];
 #pragma unroll
     for (int m = 0; m < kPixPerThread; m++) {
         const int pidx = m * kThreads + tid;  // pixel (row pidx / 40, column pidx % 40) of the tile
         const int j = ty * kBin + pidx / kBin;
-        gz[m] = kNoGroup;
+        zv[m] = kNoZ;
         if (j >= ra && j < rb) {
             const int4 g = __ldcs(&p.gbuf[(size_t)j * d.W + bx * kBin + pidx % kBin]);  // streamed: keep L1 for the grid
             if (g.w >= 0 && n_lights > 0) {
-                gz[m] = g.z / kBin;  // ray_bin_z, alternative.cpp:727
+                zv[m] = g.z;
             } else {
                 uchar4 c = make_uchar4(127, 127, 127, 0);  // miss colour, alternative.cpp:281
                 if (g.w >= 0) c = p.palette[p.atlas_color[(g.w >> 10) * kTexels + (g.w & 1023)]];
@@ -267,7 +270,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
         int mine = kNoGroup;
 #pragma unroll
         for (int m = 0; m < kPixPerThread; m++)
-            if (gz[m] > last_group) mine = min(mine, gz[m]);
+            if (group_of(zv[m]) > last_group) mine = min(mine, group_of(zv[m]));
 #pragma unroll
         for (int o = 16; o; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
         if (lane == 0 && mine != kNoGroup) atomicMin(&s.group, mine);
@@ -281,19 +284,19 @@ k_shade(const __grid_constant__ ShadeParams p) {
         // ---- compact the group's pixels into a dense list ----
         int my_n = 0;
 #pragma unroll
-        for (int m = 0; m < kPixPerThread; m++) my_n += (gz[m] == group);
+        for (int m = 0; m < kPixPerThread; m++) my_n += (group_of(zv[m]) == group);
         int pos = block_exclusive_scan(my_n, s);
         const int npix = s.scan_total;
         int lo3[3] = {0x7fffffff, 0x7fffffff, 0x7fffffff}, hi3[3] = {-0x7fffffff - 1, -0x7fffffff - 1, -0x7fffffff - 1};
 #pragma unroll
         for (int m = 0; m < kPixPerThread; m++)
-            if (gz[m] == group) {
+            if (group_of(zv[m]) == group) {
                 const int pidx = m * kThreads + tid;
                 s.pix[pos++] = (unsigned short)pidx;
-                // ray origin of this pixel (alternative.cpp:720-722), for the group's bounds
+                // ray origin of this pixel (alternative.cpp:720-722), for the group's bounds:
+                // x = column, z from the G-buffer, y = world_j - z (quirk Q11: y + z == H - row)
                 const int j = ty * kBin + pidx / kBin, i = bx * kBin + pidx % kBin;
-                const int4 g = __ldcs(&p.gbuf[(size_t)j * d.W + i]);
-                const int o3[3] = {i, g.y, g.z};
+                const int o3[3] = {i, (short)(d.H - j) - zv[m], zv[m]};
 #pragma unroll
                 for (int a = 0; a < 3; a++) {
                     lo3[a] = min(lo3[a], o3[a]);
