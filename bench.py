@@ -262,16 +262,22 @@ def ours(args):
             ms = float(t.item())
         return ms, t0, t1
 
+    sampler = ClockSampler(local) if rank == 0 else None
     with torch.cuda.stream(stream):
         ren.set_scene(h_boxes)
         step_resident()
+        # untimed pre-warm: lets the SM clock ramp from idle and gives nvidia-smi time to sample
+        t_end = time.perf_counter() + args.prewarm_ms / 1e3
+        while time.perf_counter() < t_end:
+            step_resident()
+            torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    t_load0 = time.perf_counter()
     ms, t0, t1 = timed(step_resident, args.steps, args.warmup)
     st = ren.stats()                            # per-kernel CUDA-event times of the last step
     ms_e2e, _, t1 = timed(step_e2e, args.steps, max(1, args.warmup // 2))
-    clocks = sampler.stop(t0, t1) if sampler else None
+    clocks = sampler.stop(t_load0 - args.prewarm_ms / 1e3, t1) if sampler else None  # pre-warm + timed regions: under load
 
     # per-kernel times over a few more steps, for the roofline of the dominant kernel
     shade_ms, prim_ms, build_ms = [], [], []
@@ -375,6 +381,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--prewarm-ms", type=float, default=400.0, help="untimed GPU warm-up before the W warm-up steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
