@@ -1,9 +1,9 @@
 #!/usr/bin/env python
-"""Developer tool: randomized GPU-vs-oracle parity sweep (beyond the fixed seeds of tests/).
+"""Checker (not collected by pytest; run by hand on a B200): randomized GPU-vs-oracle parity sweep (beyond the fixed seeds of tests/).
 Exercises the exact-output optimisations (shared walks, de-dup, shaft cull, near/far slab path)
 on many scene shapes: dense/sparse, cubes/ragged boxes, lights inside/outside/on surfaces.
 
-    python tools/fuzz_parity.py [n_scenes] [first_seed]
+    python tests/fuzz_parity.py [n_scenes] [first_seed]
 """
 import os
 import sys
