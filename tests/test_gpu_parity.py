@@ -168,6 +168,17 @@ def test_random_scenes_multi_sprite_multi_light(par, oracle, seed):
     _assert_frame_equal(got, ref)
 
 
+@pytest.mark.parametrize("view", [(480, 320, 640), (640, 480, 200), (200, 40, 40), (40, 1000, 120)])
+def test_view_length_differs_from_height(par, oracle, view):
+    """The reference has view_length == view_height (alternative.cpp:118-119); the ABI takes them
+    independently, and tiny / very tall views must work too."""
+    W, H, L = view
+    rng = np.random.default_rng(W * 7 + H * 3 + L)
+    boxes, lights, _ = _random_scene(rng, W, H, L, 800, 4)
+    got, ref = _render_both(par, oracle, W, H, L, boxes, lights)
+    _assert_frame_equal(got, ref)
+
+
 def test_dense_overflowing_bins(par, oracle):
     """Quirk Q2: many entities per bin so that rings wrap (n = 8, 9, 16, 17 ... inserts)."""
     rng = np.random.default_rng(7)
