@@ -468,8 +468,9 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         y0 = y1;
                         z0 = z1;
                     }
-                    // the 4-bit counts of the sub-chunk, in batches of 8 independent loads
-                    int found = 0, boxes = 0;
+                    // the 4-bit counts of the sub-chunk, in batches of 8 independent loads; occupied bins
+                    // go straight to the shared list (the warp-uniform atomicAdd is aggregated by ptxas)
+                    int boxes = 0;
                     for (int i0 = 0; i0 < n; i0 += 8) {
                         int f[8], c[8];
 #pragma unroll
@@ -479,20 +480,13 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         }
 #pragma unroll
                         for (int u = 0; u < 8; u++)
-                            if (c[u]) {  // in-place compaction: found <= i0 + u
-                                scratch[found * kThreads + tid] = f[u] << 3 | c[u];
-                                found++;
+                            if (c[u]) {
+                                const int o = atomicAdd(&s.n_occ, 1);
+                                if (o < kListCap) s.occ[o] = (unsigned)q << 28 | (unsigned)c[u] << 25 | (unsigned)f[u];
                                 boxes += c[u];
                             }
                     }
-                    if (found) {
-                        const int o = atomicAdd(&s.n_occ, found);
-                        atomicAdd(&s.seg[q].count, boxes);
-                        for (int j = 0; j < found; j++) {
-                            const int e = scratch[j * kThreads + tid];
-                            if (o + j < kListCap) s.occ[o + j] = (unsigned)q << 28 | (unsigned)(e & 7) << 25 | (unsigned)(e >> 3);
-                        }
-                    }
+                    if (boxes) atomicAdd(&s.seg[q].count, boxes);
                 }
             }
             __syncthreads();
