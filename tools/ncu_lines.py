@@ -56,7 +56,7 @@ def main():
     ap.add_argument("--sass", action="store_true", help="list the hottest SASS instructions too")
     ap.add_argument("--by", default="samples", choices=["samples", "inst"], help="sort key")
     a = ap.parse_args()
-    raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv"], check=True,
+    raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "-k", "regex:" + a.kernel], check=True,
                          capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
