@@ -9,7 +9,7 @@ namespace par {
 struct LoaderCounters {
     int n_survivors;
     int n_inserts;
-    int max_inserts_per_bin;
+    int reserved;
     int bad_scene;  // set when an AABB would index outside the 20x40 sprite (quirk Q7)
 };
 cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,

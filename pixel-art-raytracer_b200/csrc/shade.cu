@@ -10,20 +10,22 @@
 //    starts in bin (tile x, tile y, z/40) (quirk Q11).  One CTA owns a tile, groups its pixels
 //    by z/40 ("group"), compacts each group into a dense pixel list, and walks ONCE per
 //    (group, light) — for a whole batch of lights at a time:
-//      phase 1   one thread per run of 8 walk steps: the fp32 position chain is accumulated
-//                sequentially exactly as the reference does (quirk Q15); the 7 probes of a step
-//                collapse to the distinct bins among them; occupied bins (1-bit occupancy mask,
-//                L1 resident) are appended to a shared list;
-//      phase 1b  one lane per occupied bin: fetch its count;
-//      phase 2   one lane per (occupied bin, slot): entity -> box, de-duplicated per light with
-//                a shared-memory hash set (testing a box twice cannot change an OR), written as
-//                float lo/hi corners into the light's segment of a shared box list;
-//      phase 3   one lane per pixel of the group: for every light of the batch, the Lambert
-//                term and — only when it is > 0 (quirk Q19) — a loop of slab tests over that
-//                light's boxes: unbounded-line semantics (Q14), the self-entity skip (Q17), the
-//                start-bin skip (Q16) already applied in phase 1, and std::min/std::max NaN
-//                semantics (Q13) reproduced exactly: warps in which no lane can produce a NaN
-//                (no zero/NaN direction component) use FMNMX, the others the literal ternaries.
+//      walk    one thread per run of steps: the fp32 position chain is accumulated sequentially
+//              exactly as the reference does (quirk Q15); the 7 probes of a step collapse to the
+//              distinct bins among them; their 4-bit counts are fetched in batches of independent
+//              loads and occupied bins are appended to a shared list;
+//      gather  a warp scan expands the occupied bins into dense (bin, slot) lanes: entity ->
+//              de-duplicate per light (shared-memory hash set; testing a box twice cannot change
+//              an OR) -> box -> shaft cull (shaft.cuh: boxes no ray of the group can hit) -> float
+//              corners in the light's segment of a shared box list;
+//      shade   one lane per pixel of the group: for every light of the batch, the Lambert term
+//              and — only when it is > 0 (quirk Q19) — a loop of slab tests over that light's
+//              boxes: unbounded-line semantics (Q14), the self-entity skip (Q17), the start-bin
+//              skip (Q16) already applied in the walk, and std::min/std::max NaN semantics (Q13)
+//              reproduced exactly: when the light lies strictly outside the group's origin bounds
+//              no NaN can arise and the boxes are stored as (near, far) corners (6 FADD + 6 FMUL +
+//              2 FMNMX3 per box); otherwise warps without a zero/NaN direction component use
+//              FMNMX and the rest the literal ternaries.
 //    Batches that do not fit the shared lists are split (fewer lights, then fewer steps of
 //    one light); the shadow state of a split light is carried between rounds.
 //  * Finished RGBA8 pixels are staged in shared memory and leave as 16-byte stores.
