@@ -84,6 +84,7 @@ struct ShadeSmem {
     int scan_total;
     int group;
     int n_occ;
+    int overflow;  // a segment kept more boxes than its share of the list: redo the round with fewer segments
     int org_min[3], org_max[3];  // actual bounds of the current group's ray origins (shaft cull)
     int n_items;
     int run;  // walk steps per phase-1 thread this round
@@ -413,6 +414,7 @@ k_shade(const __grid_constant__ ShadeParams p) {
                 s.n_items = items;
                 s.run = run;
                 s.n_occ = 0;
+                s.overflow = 0;
             }
             __syncthreads();
             mark(kPhSetup);
@@ -494,35 +496,35 @@ k_shade(const __grid_constant__ ShadeParams p) {
             __syncthreads();
             mark(kPhWalk);
             const int n_occ = s.n_occ;  // every occupied bin holds >= 1 box, so n_occ <= sum of counts
-            // D. how many leading segments fit the box list?  (every thread, redundantly)
+            // D. how many leading segments go into this round?  (every thread, redundantly)
+            // The de-duplication set must stay sparse (candidates <= 3/4 of its slots) and the
+            // occupied-bin list must be complete.  The box list itself is shared out evenly: after
+            // de-duplication and the shaft cull a segment keeps a small fraction of its candidates,
+            // so each of the n_fit segments gets room for min(candidates, kListCap / n_fit) boxes;
+            // if one needs more, the round is redone with half the segments.
             n_fit = 0;
             {
                 int total = 0;
-                while (n_fit < nseg && total + s.seg[n_fit].count <= kListCap) {
+                while (n_fit < nseg && total + s.seg[n_fit].count <= kHashSize * 3 / 4) {
                     total += s.seg[n_fit].count;
                     n_fit++;
                 }
             }
-            if (n_fit > 0 && n_occ > kListCap) {
-                // bins of the fitting segments may have been dropped from the list: redo the walk for
-                // exactly those segments (they fit, so nothing is dropped next time)
-                nseg_try = n_fit;
-                continue;
-            }
-            if (tid < n_fit) {  // base of segment tid in the box list
-                int base = 0;
-                for (int q = 0; q < tid; q++) base += s.seg[q].count;
-                s.seg[tid].base = base;
-            }
             mark(kPhDecide);
-            if (n_fit == 0) {  // shrink: fewer lights first, then fewer steps of the first light
-                if (nseg_try > 1) {
+            if (n_fit == 0 || n_occ > kListCap) {  // shrink: fewer lights first, then fewer steps of the first light
+                if (nseg > 1) {
                     nseg_try = max(1, nseg / 2);
                 } else {
                     const int ka = s.seg[0].ka, kb = s.seg[0].kb;
                     kb_try = ka + max(1, (kb - ka) / 2);
                 }
                 continue;
+            }
+            const int share = kListCap / n_fit;
+            if (tid < n_fit) {  // base of segment tid in the box list
+                int base = 0;
+                for (int q = 0; q < tid; q++) base += min(s.seg[q].count, share);
+                s.seg[tid].base = base;
             }
 
             // E. phase 2: one lane per candidate slot.  Each warp takes 32 occupied bins, scans their
@@ -595,13 +597,27 @@ k_shade(const __grid_constant__ ShadeParams p) {
                         if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
                     }
                     int base = 0;
-                    for (int r = 0; r < q; r++) base += s.seg[r].count;
-                    const int at = base + atomicAdd(&s.seg[q].fill, 1);
-                    store_box(s, at, b, ent, s.seg[q].octant);
+                    for (int r = 0; r < q; r++) base += min(s.seg[r].count, share);
+                    const int nth = atomicAdd(&s.seg[q].fill, 1);
+                    if (nth >= min(s.seg[q].count, share)) {
+                        s.overflow = 1;
+                        continue;
+                    }
+                    store_box(s, base + nth, b, ent, s.seg[q].octant);
                 }
             }
             __syncthreads();
             mark(kPhGather);
+            if (s.overflow) {  // some segment kept more than its share: fewer segments, then fewer steps
+                if (n_fit > 1) {
+                    nseg_try = max(1, n_fit / 2);
+                } else {
+                    const int ka = s.seg[0].ka, kb = s.seg[0].kb;
+                    kb_try = ka + max(1, (kb - ka) / 2);
+                    nseg_try = 1;
+                }
+                continue;
+            }
             if (p.phase_cycles && tid == 0) {  // debug: candidate boxes found / kept after de-dup + cull
                 unsigned long long found = 0, kept = 0;
                 for (int q = 0; q < n_fit; q++) {
