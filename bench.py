@@ -192,7 +192,14 @@ def ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    trace_on = bool(os.environ.get("PAR_BENCH_TRACE"))
+
+    def trace(msg):
+        if trace_on:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     W, H, L, desc, boxes, lights = make_workload(par, args.workload)
     n_lights = len(lights)
     from par_b200.bands import gather_stripes, owned_rows
@@ -212,13 +219,38 @@ def ours(args):
     h_frame = par.pinned_empty((H, W), par.COLOR) if rank == 0 else None
     t_hframe = torch.from_numpy(h_frame.view(np.uint8).reshape(-1)) if rank == 0 else None
 
+    # Frame exchange at N > 1.  "peer" (default): the shade kernel stores its finished stripes
+    # straight into every rank's raster frame through CUDA-IPC-mapped peer memory (NVLink), and a
+    # tiny all-reduce is the barrier.  "nccl": stripe-major staging + in-place all-gather + un-stripe.
+    exchange = "none" if world == 1 else args.exchange
+    token = torch.zeros(1, dtype=torch.int32, device=dev)
+    if exchange == "peer":
+        try:
+            handles = [None] * world
+            dist.all_gather_object(handles, ren.peer_export())
+            for r in range(world):
+                if r != rank:
+                    ren.peer_import(r, handles[r])
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+        except Exception as e:  # no IPC / no peer access on this box: use the NCCL gather
+            if rank == 0:
+                print(f"bench.py: peer exchange unavailable ({e}); using nccl", file=sys.stderr)
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            exchange = "nccl"
+    trace(f"exchange = {exchange}")
+
     def render_and_gather():
         if world == 1:
             ren.render_device(lights, frame.data_ptr())
-            return
-        ren.render_device_striped(lights, staging.data_ptr())  # my stripes, contiguous in staging
-        gather_stripes(staging, world, rank)                    # in-place NCCL all-gather over NVLink
-        ren.unstripe_device(staging.data_ptr(), frame.data_ptr())  # staging -> raster frame
+        elif exchange == "peer":
+            ren.render_device_peers(lights)      # my stripes -> my frame and, in place, every peer's frame
+            dist.all_reduce(token)               # barrier: every rank's kernel (and its remote stores) is done
+        else:
+            ren.render_device_striped(lights, staging.data_ptr())  # my stripes, contiguous in staging
+            gather_stripes(staging, world, rank)                    # in-place NCCL all-gather over NVLink
+            ren.unstripe_device(staging.data_ptr(), frame.data_ptr())  # staging -> raster frame
 
     def step_resident():
         ren.rebuild_grid()                       # device scene loader on the resident scene
@@ -230,7 +262,11 @@ def ours(args):
             ren.render(lights, out=h_frame)      # the drop-in call: render + D2H into a host frame
             return
         render_and_gather()
-        if rank == 0:
+        if exchange == "peer":
+            if rank == 0:
+                ren.read_frame(h_frame)          # D2H of the finished frame (it lives in the context's frame)
+            dist.all_reduce(token)               # nobody starts overwriting frames before the reader is done
+        elif rank == 0:
             t_hframe.copy_(frame, non_blocking=True)  # D2H of the gathered frame
 
     def barrier():
@@ -266,17 +302,31 @@ def ours(args):
     with torch.cuda.stream(stream):
         ren.set_scene(h_boxes)
         step_resident()
-        # untimed pre-warm: lets the SM clock ramp from idle and gives nvidia-smi time to sample
-        t_end = time.perf_counter() + args.prewarm_ms / 1e3
-        while time.perf_counter() < t_end:
+        trace("first step enqueued")
+        torch.cuda.synchronize(dev)
+        # untimed pre-warm: lets the SM clock ramp from idle and gives nvidia-smi time to sample.
+        # The number of steps is the same on every rank (the steps contain collectives).
+        t_a = time.perf_counter()
+        for _ in range(5):
             step_resident()
-            torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
+        n_pre = torch.tensor([int(args.prewarm_ms / 1e3 / max(time.perf_counter() - t_a, 1e-6) * 5) + 1],
+                             dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(n_pre, op=dist.ReduceOp.MAX)
+        for i in range(min(int(n_pre.item()), 100000)):
+            step_resident()
+            if i % 8 == 7:
+                torch.cuda.synchronize(dev)
     torch.cuda.synchronize(dev)
+    trace("pre-warm done")
 
     t_load0 = time.perf_counter()
     ms, t0, t1 = timed(step_resident, args.steps, args.warmup)
     st = ren.stats()                            # per-kernel CUDA-event times of the last step
+    trace("resident timing done")
     ms_e2e, _, t1 = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    trace("e2e timing done")
     clocks = sampler.stop(t_load0 - args.prewarm_ms / 1e3, t1) if sampler else None  # pre-warm + timed regions: under load
 
     # per-kernel times over a few more steps, for the roofline of the dominant kernel
@@ -289,6 +339,13 @@ def ours(args):
             shade_ms.append(s["ms_shade"])
             prim_ms.append(s["ms_primary"])
             build_ms.append(s["ms_grid_build"])
+    if world > 1:
+        # orderly teardown: nobody frees a frame another rank still has mapped
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        ren.close()
+        dist.barrier()
+        trace("contexts closed")
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -337,13 +394,15 @@ def ours(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {desc}", "view": [W, H, L], "n_entities": int(len(boxes)),
                    "n_lights": int(n_lights), "rays_per_frame": rays_frame,
-                   "parallelism": (f"interleaved 40-row stripes x{world} + in-place NCCL all-gather of the RGBA8 frame"
-                                   if world > 1 else "1 GPU"),
+                   "parallelism": ("1 GPU" if world == 1 else
+                                   f"interleaved 40-row stripes x{world}, frame exchange fused into the shade kernel "
+                                   "(peer-memory stores over NVLink + all-reduce barrier)" if exchange == "peer" else
+                                   f"interleaved 40-row stripes x{world} + in-place NCCL all-gather of the RGBA8 frame"),
                    "l2": "flushed between timed steps (256 MB fill)", "frames_per_s": round(1e3 * args.steps / ms, 2)},
         "e2e": {"value": round(e2e, 1), "unit": "Mrays/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "frames_per_s": round(1e3 * args.steps / ms_e2e, 2),
                 "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4)},
-        "gpu_launches": ((4 if world == 1 else 5) * args.steps) * world,
+        "gpu_launches": ((4 if world == 1 or exchange == "peer" else 5) * args.steps) * world,
         "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
                        "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},
         "roofline": roofline, "clocks": clocks,
@@ -381,6 +440,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1 frame exchange: fused peer-memory stores (default) or NCCL all-gather")
     ap.add_argument("--prewarm-ms", type=float, default=400.0, help="untimed GPU warm-up before the W warm-up steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

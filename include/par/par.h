@@ -166,6 +166,22 @@ int par_render_device_striped(par_ctx* ctx, const par_light* lights, int n_light
 size_t par_staging_bytes(const par_ctx* ctx);
 int par_unstripe_device(par_ctx* ctx, const void* d_staging, void* d_rgba);
 
+/* Fused frame exchange (striped contexts): k_shade stores every finished 16-byte chunk of its
+ * stripes into its own raster frame AND, in place, into the raster frames of all other ranks
+ * through peer memory (NVLink / NVSwitch), so the frame is complete on every GPU as soon as all
+ * ranks' kernels have finished — a barrier replaces the all-gather + un-stripe passes.
+ *   one process per GPU : par_peer_export (64-byte CUDA IPC handle of the own frame), exchange the
+ *                         handles, par_peer_import(rank, handle) for every other rank;
+ *   one process, N GPUs : par_peer_set(rank, par_device_frame(other ctx)) after enabling peer access.
+ * par_render_device_peers renders asynchronously; the caller provides the cross-rank barrier. */
+int par_peer_export(par_ctx* ctx, void* handle64);
+int par_peer_import(par_ctx* ctx, int rank, const void* handle64);
+int par_peer_set(par_ctx* ctx, int rank, void* d_peer_frame);
+int par_render_device_peers(par_ctx* ctx, const par_light* lights, int n_lights);
+/* Enqueue a D2H copy of the context's whole raster frame on its stream (asynchronous for pinned
+ * memory; par_sync or stream ordering before reading the host buffer). */
+int par_read_frame(par_ctx* ctx, par_color* out_rgba);
+
 /* Device pointer of the context's own W*H*4 frame buffer. */
 void* par_device_frame(par_ctx* ctx);
 

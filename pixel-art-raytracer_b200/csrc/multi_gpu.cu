@@ -1,10 +1,13 @@
 // multi_gpu.cu — single-process multi-GPU mode of the C ABI (par_multi_*): the image is split
 // into interleaved 40-row stripes (tile row t belongs to device t % n — the per-row cost of the
-// shadow walks varies strongly over the image, so contiguous bands scale badly), one par_ctx
-// per device renders its stripes STRIPE-MAJOR into a staging frame in its own HBM (its output
-// is one contiguous block), one in-place ncclAllGather over NVLink completes the staging frame
-// on every device and a copy kernel turns it into the raster frame.  The
-// scene/grid is replicated: a shadow ray may visit any bin.
+// shadow walks varies strongly over the image, so contiguous bands scale badly); the scene/grid
+// is replicated (a shadow ray may visit any bin).  Frame exchange:
+//  * preferred — FUSED over peer memory: every device maps the raster frames of all others and
+//    its shade kernel stores each finished 16-byte chunk into all of them (posted writes over
+//    NVLink / NVSwitch); cross-device events make the frames complete — no pass over the frame;
+//  * fallback (no peer access, or PAR_MULTI_EXCHANGE=nccl) — every device renders its stripes
+//    STRIPE-MAJOR into a staging frame (its output is one contiguous block), one in-place
+//    ncclAllGather completes the staging frames and a copy kernel turns them into raster frames.
 //
 // NCCL is loaded lazily with dlopen("libnccl.so.2") so that libpar_b200.so itself has no
 // link-time NCCL dependency and the one-GPU path never touches it.  (bench.py's torchrun mode
@@ -13,6 +16,7 @@
 #include <nccl.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -57,7 +61,9 @@ struct par_multi {
     int W = 0, H = 0;
     par_ctx* ctx[8] = {};
     int device[8] = {};
-    void* staging[8] = {};  // stripe-major frames, one per device
+    void* staging[8] = {};  // stripe-major frames, one per device (NCCL path only)
+    bool peer = false;      // fused exchange: every device writes its stripes straight into all frames
+    cudaEvent_t done[8] = {};
     ncclComm_t comm[8] = {};
     bool have_comm = false;
 };
@@ -70,6 +76,13 @@ void par_multi_destroy(par_multi* m) {
     if (!m) return;
     for (int i = 0; i < m->n; i++) {
         if (m->have_comm && m->comm[i]) g_nccl.CommDestroy(m->comm[i]);
+        if (m->done[i]) {
+            int prev = 0;
+            cudaGetDevice(&prev);
+            cudaSetDevice(m->device[i]);
+            cudaEventDestroy(m->done[i]);
+            cudaSetDevice(prev);
+        }
         if (m->staging[i]) {
             int prev = 0;
             cudaGetDevice(&prev);
@@ -102,7 +115,34 @@ int par_multi_create(par_multi** out, const par_config* cfg, const int* devices,
         c.stripe_index = i;
         m->device[i] = devices[i];
         int rc = par_create(&m->ctx[i], &c);
-        if (rc == PAR_OK && n_devices > 1) {
+        if (rc != PAR_OK) {
+            m->n = i + 1;
+            par_multi_destroy(m);
+            return rc;
+        }
+    }
+    // Preferred exchange: peer memory.  Every device maps the raster frames of all others and its
+    // shade kernel stores finished pixels into all of them (par_render_device_peers).
+    m->peer = n_devices > 1;
+    if (const char* e = getenv("PAR_MULTI_EXCHANGE"))  // "nccl" forces the all-gather path (tests, A/B)
+        if (!strcmp(e, "nccl")) m->peer = false;
+    for (int i = 0; i < n_devices && m->peer; i++)
+        for (int j = 0; j < n_devices && m->peer; j++) {
+            int can = 1;
+            if (i != j && (cudaDeviceCanAccessPeer(&can, devices[i], devices[j]) != cudaSuccess || !can)) m->peer = false;
+        }
+    for (int i = 0; i < n_devices && m->peer; i++) {
+        for (int j = 0; j < n_devices && m->peer; j++)
+            if (i != j && par_peer_set(m->ctx[i], j, par_device_frame(m->ctx[j])) != PAR_OK) m->peer = false;
+        int prev = 0;
+        cudaGetDevice(&prev);
+        cudaSetDevice(devices[i]);
+        if (cudaEventCreateWithFlags(&m->done[i], cudaEventDisableTiming) != cudaSuccess) m->peer = false;
+        cudaSetDevice(prev);
+    }
+    for (int i = 0; i < n_devices; i++) {
+        int rc = PAR_OK;
+        if (n_devices > 1 && !m->peer) {
             int prev = 0;
             cudaGetDevice(&prev);
             cudaSetDevice(devices[i]);
@@ -114,12 +154,11 @@ int par_multi_create(par_multi** out, const par_config* cfg, const int* devices,
             cudaSetDevice(prev);
         }
         if (rc != PAR_OK) {
-            m->n = i + 1;
             par_multi_destroy(m);
             return rc;
         }
     }
-    if (n_devices > 1) {
+    if (n_devices > 1 && !m->peer) {
         if (!g_nccl.load()) {
             snprintf(g_multi_err, sizeof g_multi_err, "par_multi_create: cannot load libnccl.so.2: %s", dlerror());
             par_multi_destroy(m);
@@ -166,6 +205,21 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
     if (m->n == 1) {
         int rc = par_render_device(m->ctx[0], lights, n_lights, nullptr);
         if (rc != PAR_OK) return rc;
+    } else if (m->peer) {
+        int prev = 0;
+        cudaGetDevice(&prev);
+        for (int i = 0; i < m->n; i++) {  // asynchronous: all devices render and scatter concurrently
+            int rc = par_render_device_peers(m->ctx[i], lights, n_lights);
+            if (rc != PAR_OK) return rc;
+            cudaSetDevice(m->device[i]);
+            cudaEventRecord(m->done[i], static_cast<cudaStream_t>(par_get_stream(m->ctx[i])));
+        }
+        for (int i = 0; i < m->n; i++) {  // a frame is complete once EVERY device has finished writing into it
+            cudaSetDevice(m->device[i]);
+            for (int j = 0; j < m->n; j++)
+                if (j != i) cudaStreamWaitEvent(static_cast<cudaStream_t>(par_get_stream(m->ctx[i])), m->done[j], 0);
+        }
+        cudaSetDevice(prev);
     } else {
         for (int i = 0; i < m->n; i++) {  // asynchronous: all devices render their stripes concurrently
             int rc = par_render_device_striped(m->ctx[i], lights, n_lights, m->staging[i]);

@@ -123,6 +123,10 @@ struct par_ctx {
     bool scene_set = false, frame_valid = false, build_timed = false, frame_timed = false;
     int launches_build = 0, launches_frame = 0, last_n_lights = 0;
     float ambient = 0.25f;
+    // fused multi-GPU frame exchange: raster frames of the other ranks, mapped into this process
+    uchar4* peer_frame[8] = {};
+    bool peer_is_ipc[8] = {};
+    int n_peers = 0;  // entries of peer_frame in use (own rank's entry stays NULL)
     float last_kernel_ms = 0.f;  // primary + shade of the previous par_render (pipelining heuristic)
     int readback_chunks = 3;  // row chunks of the pipelined readback (PAR_READBACK_CHUNKS overrides)
     int debug_flags = 0;  // from the PAR_DEBUG_FLAGS environment variable (developer A/B switches)
@@ -278,6 +282,8 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_atlas_normal);
     cudaFree(c->d_atlas_color);
     cudaFree(c->d_palette);
+    for (int r = 0; r < 8; r++)
+        if (c->peer_frame[r] && c->peer_is_ipc[r]) cudaIpcCloseMemHandle(c->peer_frame[r]);
     cudaFree(c->d_tile_ngroups);
     cudaFree(c->d_groups);
     cudaFree(c->d_table);
@@ -441,7 +447,7 @@ int par_rebuild_grid(par_ctx* c) {
 // rendering of chunk k+1 on a second stream — at 4K the 33 MB readback takes about as long as
 // the kernels, so the drop-in call is roughly max(render, copy) instead of their sum.
 static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4* d_out, par_color* host_out,
-                       bool striped_out = false) {
+                       bool striped_out = false, bool to_peers = false) {
     if (!c || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
         return fail(PAR_ERR_INVALID_ARG, "par_render: bad argument (at most 64 lights)%s%s");
     if (!c->scene_set || c->n_sprites == 0)
@@ -518,6 +524,9 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     sp.table = use_walks ? c->d_table : nullptr;
     sp.pool = c->d_pool;
     sp.out_stripe_T = striped_out ? (d.HH + d.stripe_n - 1) / d.stripe_n : 0;
+    sp.n_peer_out = 0;
+    for (int r = 0; r < 8 && to_peers; r++)
+        if (c->peer_frame[r]) sp.peer_out[sp.n_peer_out++] = c->peer_frame[r];
     memset(sp.lights, 0, sizeof sp.lights);
     for (int l = 0; l < n_lights; l++)
         sp.lights[l] = make_short4(lights[l].x, lights[l].y, lights[l].z, lights[l].radius);
@@ -595,6 +604,70 @@ int par_render_device_striped(par_ctx* c, const par_light* lights, int n_lights,
     if (c->d.row0 != 0 || c->d.row1 != c->d.H)
         return fail(PAR_ERR_INVALID_ARG, "par_render_device_striped: the context must cover the whole frame%s%s");
     return render_impl(c, lights, n_lights, static_cast<uchar4*>(d_staging), nullptr, true);
+}
+
+// ---- fused frame exchange over peer memory -------------------------------------------------------
+int par_peer_export(par_ctx* c, void* handle64) {
+    if (!c || !handle64) return fail(PAR_ERR_INVALID_ARG, "par_peer_export: null argument%s%s");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard(c->cfg.device);
+    cudaIpcMemHandle_t h;
+    PAR_CUDA(cudaIpcGetMemHandle(&h, c->d_frame));
+    memcpy(handle64, &h, sizeof h);
+    return PAR_OK;
+}
+
+static int set_peer(par_ctx* c, int rank, uchar4* ptr, bool ipc) {
+    if (rank < 0 || rank >= 8 || rank == c->d.stripe_i)
+        return fail(PAR_ERR_INVALID_ARG, "par_peer: rank must be another stripe index below 8%s%s");
+    if (c->peer_frame[rank] && c->peer_is_ipc[rank]) cudaIpcCloseMemHandle(c->peer_frame[rank]);
+    if (!c->peer_frame[rank]) c->n_peers++;
+    c->peer_frame[rank] = ptr;
+    c->peer_is_ipc[rank] = ipc;
+    return PAR_OK;
+}
+
+int par_peer_import(par_ctx* c, int rank, const void* handle64) {
+    if (!c || !handle64) return fail(PAR_ERR_INVALID_ARG, "par_peer_import: null argument%s%s");
+    DeviceGuard guard(c->cfg.device);
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    void* ptr = nullptr;
+    PAR_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return set_peer(c, rank, static_cast<uchar4*>(ptr), true);
+}
+
+int par_peer_set(par_ctx* c, int rank, void* d_peer_frame) {
+    if (!c || !d_peer_frame) return fail(PAR_ERR_INVALID_ARG, "par_peer_set: null argument%s%s");
+    DeviceGuard guard(c->cfg.device);
+    cudaPointerAttributes attr;
+    PAR_CUDA(cudaPointerGetAttributes(&attr, d_peer_frame));
+    if (attr.type != cudaMemoryTypeDevice)
+        return fail(PAR_ERR_INVALID_ARG, "par_peer_set: not a device pointer%s%s");
+    if (attr.device != c->cfg.device) {
+        int can = 0;
+        PAR_CUDA(cudaDeviceCanAccessPeer(&can, c->cfg.device, attr.device));
+        if (!can) return fail(PAR_ERR_NO_DEVICE, "par_peer_set: no peer access between the two devices%s%s");
+        cudaError_t e = cudaDeviceEnablePeerAccess(attr.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PAR_CUDA(e);
+        cudaGetLastError();
+    }
+    return set_peer(c, rank, static_cast<uchar4*>(d_peer_frame), false);
+}
+
+int par_read_frame(par_ctx* c, par_color* out_rgba) {
+    if (!c || !out_rgba) return fail(PAR_ERR_INVALID_ARG, "par_read_frame: null argument%s%s");
+    DeviceGuard guard(c->cfg.device);
+    PAR_CUDA(cudaMemcpyAsync(out_rgba, c->d_frame, sizeof(par_color) * (size_t)c->d.W * c->d.H,
+                             cudaMemcpyDeviceToHost, c->stream));
+    return PAR_OK;
+}
+
+int par_render_device_peers(par_ctx* c, const par_light* lights, int n_lights) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_render_device_peers: null context%s%s");
+    if (c->n_peers != c->d.stripe_n - 1)
+        return fail(PAR_ERR_STATE, "par_render_device_peers: import the frames of all other ranks first%s%s");
+    return render_impl(c, lights, n_lights, c->d_frame, nullptr, false, true);
 }
 
 int par_unstripe_device(par_ctx* c, const void* d_staging, void* d_rgba) {

@@ -79,6 +79,8 @@ struct ShadeParams {
     float ambient;
     int tile_row_first;
     int out_stripe_T;  // 0: raster output; T > 0: stripe-major staging, T stripes per rank
+    int n_peer_out;    // fused frame exchange: every finished 16-byte chunk is also stored, in place, into
+    uchar4* peer_out[7];  //   the raster frames of the other GPUs (peer memory over NVLink / NVSwitch)
     int debug_flags;   // bit 0: disable the shaft cull, bit 2: ignore precomputed walks (A/B measurements only)
     const int* tile_ngroups;  // precomputed walks (walks.cu); NULL = shade walks itself
     const int2* table;

@@ -728,7 +728,11 @@ k_shade(const __grid_constant__ ShadeParams p) {
         const uint4 px = *reinterpret_cast<const uint4*>(&s.out[4 * v]);
         // raster row, or the row's slot in the stripe-major staging frame (rank-contiguous)
         const int jo = p.out_stripe_T ? ((ty % d.stripe_n) * p.out_stripe_T + ty / d.stripe_n) * kBin + (j - ty * kBin) : j;
-        *reinterpret_cast<uint4*>(&p.out[(size_t)jo * d.W + bx * kBin + 4 * (v % (kBin / 4))]) = px;
+        const size_t at = (size_t)jo * d.W + bx * kBin + 4 * (v % (kBin / 4));
+        *reinterpret_cast<uint4*>(&p.out[at]) = px;
+        // Fused exchange: the same chunk goes straight into every peer GPU's frame (posted writes over
+        // NVLink), so no all-gather pass over the frame is needed afterwards — only a barrier.
+        for (int r = 0; r < p.n_peer_out; r++) *reinterpret_cast<uint4*>(&p.peer_out[r][at]) = px;
     }
 }
 

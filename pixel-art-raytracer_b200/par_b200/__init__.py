@@ -38,6 +38,7 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_multi_last_error", "par_sync", "par_alloc_host", "par_free_host", "par_set_atlas", "par_set_scene",
            "par_rebuild_grid", "par_render", "par_render_device", "par_device_frame",
            "par_render_device_striped", "par_staging_bytes", "par_unstripe_device",
+           "par_peer_export", "par_peer_import", "par_peer_set", "par_render_device_peers", "par_read_frame",
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
            "par_debug_phase_timing",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
@@ -112,6 +113,11 @@ def lib():
         L.par_staging_bytes.argtypes = [vp]
         L.par_staging_bytes.restype = C.c_size_t
         L.par_unstripe_device.argtypes = [vp, vp, vp]
+        L.par_peer_export.argtypes = [vp, vp]
+        L.par_peer_import.argtypes = [vp, i32, vp]
+        L.par_peer_set.argtypes = [vp, i32, vp]
+        L.par_render_device_peers.argtypes = [vp, vp, i32]
+        L.par_read_frame.argtypes = [vp, vp]
         L.par_device_frame.argtypes = [vp]
         L.par_device_frame.restype = vp
         L.par_get_gbuffer.argtypes = [vp, vp, vp]
@@ -285,6 +291,29 @@ class Renderer:
 
     def unstripe_device(self, d_staging: int, d_rgba: int):
         _check(lib().par_unstripe_device(self._h, d_staging, d_rgba))
+
+    def peer_export(self) -> bytes:
+        """64-byte CUDA IPC handle of this context's raster frame."""
+        buf = C.create_string_buffer(64)
+        _check(lib().par_peer_export(self._h, buf))
+        return buf.raw
+
+    def peer_import(self, rank: int, handle: bytes):
+        _check(lib().par_peer_import(self._h, rank, C.create_string_buffer(handle, 64)))
+
+    def peer_set(self, rank: int, d_frame: int):
+        _check(lib().par_peer_set(self._h, rank, d_frame))
+
+    def render_device_peers(self, lights):
+        """Render own stripes into the own frame and, in place, into every imported peer frame."""
+        lights = np.ascontiguousarray(lights, LIGHT)
+        _check(lib().par_render_device_peers(self._h, _p(lights), len(lights)))
+
+    def read_frame(self, out=None):
+        """D2H of the whole raster frame, enqueued on the context's stream; call sync() before use."""
+        out = np.zeros((self.H, self.W), COLOR) if out is None else out
+        _check(lib().par_read_frame(self._h, _p(out)))
+        return out
 
     def device_frame(self) -> int:
         return lib().par_device_frame(self._h)

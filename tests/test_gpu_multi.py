@@ -40,6 +40,53 @@ def test_multi_equals_single(par, n):
     assert st["rays"] == W * H * 7
 
 
+def test_multi_nccl_fallback_path(par, monkeypatch):
+    """The NCCL all-gather path of par_multi_* (used when peer access is unavailable)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("PAR_MULTI_EXCHANGE", "nccl")
+    W, H, L = 1280, 720, 720
+    boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        one, _ = r.render(lights)
+    with par.MultiRenderer(W, H, L, [0, 1]) as m:
+        m.set_atlas()
+        m.set_scene(boxes)
+        many, _ = m.render(lights)
+    assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+
+
+def test_fused_peer_exchange_two_contexts(par):
+    """par_render_device_peers: two striped contexts on two GPUs write into each other's frames;
+    after both finish, BOTH frames equal the one-GPU frame."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H, L = 1280, 720, 720
+    boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        one, _ = r.render(lights)
+    with par.Renderer(W, H, L, device=0, stripe_count=2, stripe_index=0) as a, \
+            par.Renderer(W, H, L, device=1, stripe_count=2, stripe_index=1) as b:
+        a.peer_set(1, b.device_frame())
+        b.peer_set(0, a.device_frame())
+        for r in (a, b):
+            r.set_atlas()
+            r.set_scene(boxes)
+        for r in (a, b):
+            r.render_device_peers(lights)
+        a.sync()
+        b.sync()
+        fa, fb = a.read_frame(), b.read_frame()
+        a.sync()
+        b.sync()
+    assert np.array_equal(one.view(np.uint32), fa.view(np.uint32))
+    assert np.array_equal(one.view(np.uint32), fb.view(np.uint32))
+
+
 def test_multi_single_device_is_plain(par):
     W, H, L = 480, 320, 320
     with par.Renderer(W, H, L) as r:
