@@ -241,6 +241,31 @@ def ours(args):
             exchange = "nccl"
     trace(f"exchange = {exchange}")
 
+    # Host-side frame at N > 1: ONE frame in shared memory, page-locked by every rank; each rank
+    # DMAs the stripes it rendered straight into it over its own PCIe link (par_read_stripes).
+    shared = None
+    if world > 1:
+        name = [f"/dev/shm/par_bench_{os.getpid()}" if rank == 0 else None]
+        dist.broadcast_object_list(name, src=0)
+        try:
+            if rank == 0:
+                shared = par.shared_host_frame(name[0], H, W, create=True)
+            dist.barrier()
+            if rank != 0:
+                shared = par.shared_host_frame(name[0], H, W, create=False)
+            ok = torch.ones(1, dtype=torch.int32, device=dev)
+        except Exception as e:
+            trace(f"shared host frame unavailable: {e}")
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+            if rank == 0 and shared is None:
+                dist.barrier()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if rank == 0 and os.path.exists(name[0]):
+            os.unlink(name[0])                   # the mappings keep it alive
+        if int(ok.item()) == 0:
+            shared = None
+    trace(f"shared host frame: {shared is not None}")
+
     def render_and_gather():
         if world == 1:
             ren.render_device(lights, frame.data_ptr())
@@ -260,6 +285,11 @@ def ours(args):
         ren.set_scene(h_boxes)                   # H2D from pinned memory + scene loader
         if world == 1:
             ren.render(lights, out=h_frame)      # the drop-in call: render + D2H into a host frame
+            return
+        if shared is not None:
+            ren.render_device(lights)            # my stripes into my own frame: no GPU-to-GPU exchange needed
+            ren.read_stripes(shared)             # ... and from there into the shared host frame (my PCIe link)
+            dist.all_reduce(token)               # the host frame is complete when every rank's DMA is
             return
         render_and_gather()
         if exchange == "peer":
@@ -339,6 +369,30 @@ def ours(args):
             shade_ms.append(s["ms_shade"])
             prim_ms.append(s["ms_primary"])
             build_ms.append(s["ms_grid_build"])
+    # correctness spot check of what was timed (untimed): the frame the last e2e step left in host
+    # memory, and the device frame of the last resident step, equal a fresh 1-context render
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    frame_check = None
+    if rank == 0:
+        with par.Renderer(W, H, L, device=local) as chk:
+            chk.set_atlas()
+            chk.set_scene(boxes)
+            want, _ = chk.render(lights)
+        got_host = shared if shared is not None else h_frame
+        if world == 1:
+            got_dev = frame.cpu().numpy().view(par.COLOR).reshape(H, W)
+        elif exchange == "peer":
+            got_dev = ren.read_frame()
+            ren.sync()
+        else:
+            got_dev = frame.cpu().numpy().view(par.COLOR).reshape(H, W)
+        same_host = bool(np.array_equal(np.asarray(got_host).view(np.uint32), want.view(np.uint32)))
+        same_dev = bool(np.array_equal(got_dev.view(np.uint32), want.view(np.uint32)))
+        frame_check = {"host_frame_equals_1ctx_render": same_host, "device_frame_equals_1ctx_render": same_dev}
+        if not (same_host and same_dev):
+            raise SystemExit(f"bench.py: timed frames differ from a 1-context render: {frame_check}")
     if world > 1:
         # orderly teardown: nobody frees a frame another rank still has mapped
         torch.cuda.synchronize(dev)
@@ -401,11 +455,13 @@ def ours(args):
                    "l2": "flushed between timed steps (256 MB fill)", "frames_per_s": round(1e3 * args.steps / ms, 2)},
         "e2e": {"value": round(e2e, 1), "unit": "Mrays/s", "ms_per_step": round(ms_e2e / args.steps, 4),
                 "frames_per_s": round(1e3 * args.steps / ms_e2e, 2),
-                "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4)},
+                "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4),
+                "readback": ("each rank DMAs its own stripes into one shared pinned host frame (N PCIe links)"
+                             if shared is not None else "rank 0 / the one context copies the whole frame")},
         "gpu_launches": ((4 if world == 1 or exchange == "peer" else 5) * args.steps) * world,
         "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
                        "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},
-        "roofline": roofline, "clocks": clocks,
+        "roofline": roofline, "clocks": clocks, "frame_check": frame_check,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, W, H, L)

@@ -181,6 +181,17 @@ int par_render_device_peers(par_ctx* ctx, const par_light* lights, int n_lights)
 /* Enqueue a D2H copy of the context's whole raster frame on its stream (asynchronous for pinned
  * memory; par_sync or stream ordering before reading the host buffer). */
 int par_read_frame(par_ctx* ctx, par_color* out_rgba);
+/* Enqueue a D2H copy of only the rows this context OWNS (its band / interleaved stripes) into
+ * their raster position inside a full W*H host frame — one strided DMA.  With one context per
+ * GPU all pointing at the same pinned host frame (one process: par_alloc_host; several
+ * processes: shared memory + par_register_host in each), the N GPUs move the frame over their
+ * N PCIe links in parallel and no GPU-to-GPU exchange is needed for a host-side consumer
+ * (the SDL texture upload of alternative.cpp:786-788 reads host memory). */
+int par_read_stripes(par_ctx* ctx, par_color* host_frame);
+/* Page-lock / unlock host memory the caller already owns (e.g. a shared-memory frame), so that
+ * copies into it are asynchronous DMA. */
+int par_register_host(void* p, size_t bytes);
+int par_unregister_host(void* p);
 
 /* Device pointer of the context's own W*H*4 frame buffer. */
 void* par_device_frame(par_ctx* ctx);

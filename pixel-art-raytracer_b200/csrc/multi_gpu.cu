@@ -205,6 +205,7 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
     if (m->n == 1) {
         int rc = par_render_device(m->ctx[0], lights, n_lights, nullptr);
         if (rc != PAR_OK) return rc;
+        if (out_rgba && (rc = par_read_stripes(m->ctx[0], out_rgba)) != PAR_OK) return rc;
     } else if (m->peer) {
         int prev = 0;
         cudaGetDevice(&prev);
@@ -213,6 +214,8 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
             if (rc != PAR_OK) return rc;
             cudaSetDevice(m->device[i]);
             cudaEventRecord(m->done[i], static_cast<cudaStream_t>(par_get_stream(m->ctx[i])));
+            // host frame: every device ships the stripes it rendered over its own PCIe link
+            if (out_rgba && (rc = par_read_stripes(m->ctx[i], out_rgba)) != PAR_OK) return rc;
         }
         for (int i = 0; i < m->n; i++) {  // a frame is complete once EVERY device has finished writing into it
             cudaSetDevice(m->device[i]);
@@ -241,18 +244,7 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
         for (int i = 0; i < m->n; i++) {  // staging -> raster frame on every device
             int rc = par_unstripe_device(m->ctx[i], m->staging[i], par_device_frame(m->ctx[i]));
             if (rc != PAR_OK) return rc;
-        }
-    }
-    if (out_rgba) {
-        int prev = 0;
-        cudaGetDevice(&prev);
-        cudaSetDevice(m->device[0]);
-        cudaError_t ce = cudaMemcpyAsync(out_rgba, par_device_frame(m->ctx[0]), (size_t)m->W * m->H * 4,
-                                         cudaMemcpyDeviceToHost, static_cast<cudaStream_t>(par_get_stream(m->ctx[0])));
-        cudaSetDevice(prev);
-        if (ce != cudaSuccess) {
-            snprintf(g_multi_err, sizeof g_multi_err, "frame readback: %s", cudaGetErrorString(ce));
-            return PAR_ERR_CUDA;
+            if (out_rgba && (rc = par_read_stripes(m->ctx[i], out_rgba)) != PAR_OK) return rc;
         }
     }
     for (int i = 0; i < m->n; i++) {

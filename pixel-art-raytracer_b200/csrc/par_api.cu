@@ -663,6 +663,55 @@ int par_read_frame(par_ctx* c, par_color* out_rgba) {
     return PAR_OK;
 }
 
+int par_read_stripes(par_ctx* c, par_color* host_frame) {
+    if (!c || !host_frame) return fail(PAR_ERR_INVALID_ARG, "par_read_stripes: null argument%s%s");
+    DeviceGuard guard(c->cfg.device);
+    const ViewDims& d = c->d;
+    const size_t row_bytes = sizeof(par_color) * (size_t)d.W;
+    int first, count;
+    owned_tile_rows(d, first, count);
+    if (count <= 0) return PAR_OK;
+    const int n = d.stripe_n > 1 ? d.stripe_n : 1;
+    const int last = first + (count - 1) * n;
+    const bool whole_tiles = first * kBin >= d.row0 && (last + 1) * kBin <= d.row1;
+    if (n == 1) {  // a band (or the whole frame): one contiguous block
+        PAR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host_frame) + d.row0 * row_bytes,
+                                 reinterpret_cast<const char*>(c->d_frame) + d.row0 * row_bytes,
+                                 row_bytes * (size_t)(d.row1 - d.row0), cudaMemcpyDeviceToHost, c->stream));
+        return PAR_OK;
+    }
+    if (whole_tiles) {  // the owned stripes lie at a regular pitch: one strided DMA
+        const size_t pitch = row_bytes * kBin * n, off = (size_t)first * kBin * row_bytes;
+        PAR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(host_frame) + off, pitch,
+                                   reinterpret_cast<const char*>(c->d_frame) + off, pitch, row_bytes * kBin, count,
+                                   cudaMemcpyDeviceToHost, c->stream));
+        return PAR_OK;
+    }
+    for (int t = first; t <= last; t += n) {  // band edges inside a tile row: one copy per clipped stripe
+        const int r0 = std::max(t * kBin, d.row0), r1 = std::min((t + 1) * kBin, d.row1);
+        if (r1 <= r0) continue;
+        PAR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host_frame) + r0 * row_bytes,
+                                 reinterpret_cast<const char*>(c->d_frame) + r0 * row_bytes,
+                                 row_bytes * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->stream));
+    }
+    return PAR_OK;
+}
+
+int par_register_host(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(PAR_ERR_INVALID_ARG, "par_register_host: null argument%s%s");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(PAR_ERR_CUDA, "par_register_host: %s%s", cudaGetErrorString(e));
+    }
+    return PAR_OK;
+}
+
+int par_unregister_host(void* p) {
+    if (p && cudaHostUnregister(p) != cudaSuccess) cudaGetLastError();
+    return PAR_OK;
+}
+
 int par_render_device_peers(par_ctx* c, const par_light* lights, int n_lights) {
     if (!c) return fail(PAR_ERR_INVALID_ARG, "par_render_device_peers: null context%s%s");
     if (c->n_peers != c->d.stripe_n - 1)

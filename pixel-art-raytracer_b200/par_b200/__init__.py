@@ -39,6 +39,7 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_rebuild_grid", "par_render", "par_render_device", "par_device_frame",
            "par_render_device_striped", "par_staging_bytes", "par_unstripe_device",
            "par_peer_export", "par_peer_import", "par_peer_set", "par_render_device_peers", "par_read_frame",
+           "par_read_stripes", "par_register_host", "par_unregister_host",
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
            "par_debug_phase_timing",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
@@ -118,6 +119,9 @@ def lib():
         L.par_peer_set.argtypes = [vp, i32, vp]
         L.par_render_device_peers.argtypes = [vp, vp, i32]
         L.par_read_frame.argtypes = [vp, vp]
+        L.par_read_stripes.argtypes = [vp, vp]
+        L.par_register_host.argtypes = [vp, C.c_size_t]
+        L.par_unregister_host.argtypes = [vp]
         L.par_device_frame.argtypes = [vp]
         L.par_device_frame.restype = vp
         L.par_get_gbuffer.argtypes = [vp, vp, vp]
@@ -209,6 +213,22 @@ def pinned_empty(shape, dtype) -> np.ndarray:
 
 
 _PINNED: dict[int, int] = {}
+
+
+def shared_host_frame(path: str, H: int, W: int, create: bool) -> np.ndarray:
+    """(H, W) COLOR frame in a shared-memory file, page-locked in THIS process (par_register_host):
+    several one-GPU processes DMA their stripes into the same host frame (par_read_stripes)."""
+    n = H * W * COLOR.itemsize
+    if create:
+        with open(path, "wb") as f:
+            f.truncate(n)
+    arr = np.memmap(path, dtype=COLOR, mode="r+", shape=(H, W))
+    _check(lib().par_register_host(arr.ctypes.data, n))
+    return arr
+
+
+def release_shared_host_frame(arr: np.ndarray):
+    lib().par_unregister_host(arr.ctypes.data)
 
 
 # ---- the render path ------------------------------------------------------------------------
@@ -314,6 +334,12 @@ class Renderer:
         out = np.zeros((self.H, self.W), COLOR) if out is None else out
         _check(lib().par_read_frame(self._h, _p(out)))
         return out
+
+    def read_stripes(self, host_frame):
+        """D2H of the rows this context owns into their place in a full (H, W) host frame (async)."""
+        assert host_frame.shape == (self.H, self.W) and host_frame.dtype == COLOR and host_frame.flags.c_contiguous
+        _check(lib().par_read_stripes(self._h, _p(host_frame)))
+        return host_frame
 
     def device_frame(self) -> int:
         return lib().par_device_frame(self._h)

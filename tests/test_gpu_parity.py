@@ -358,6 +358,50 @@ def test_stripes_reassemble(par, n):
     assert np.array_equal(unstripe(staging, W, H, n).cpu().numpy(), full.view(np.uint8).reshape(-1))
 
 
+@pytest.mark.parametrize("n,band", [(1, None), (2, None), (3, None), (8, None), (1, (97, 333)), (3, (50, 430))])
+def test_read_stripes_into_one_host_frame(par, n, band):
+    """par_read_stripes: every context copies only the rows it owns into ONE shared host frame
+    (the parallel PCIe readback of the multi-GPU host path); together they give the full frame.
+    Rows nobody owns (outside a band) stay untouched."""
+    W, H, L = 640, 480, 480
+    boxes, lights = par.scene_synthetic(W, H, L, n=1500, n_lights=5)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        full, _ = r.render(lights)
+    a, b = band or (0, H)
+    host = par.pinned_empty((H, W), par.COLOR)
+    _u32(host)[:] = 0xDEADBEEF
+    for i in range(n):
+        kw = dict(stripe_count=n, stripe_index=i) if n > 1 else {}
+        with par.Renderer(W, H, L, row_begin=a, row_end=b, **kw) as r:
+            r.set_atlas()
+            r.set_scene(boxes)
+            r.render_device(lights)
+            r.read_stripes(host)
+            r.sync()
+    assert np.array_equal(_u32(host[a:b]), _u32(full[a:b]))
+    assert (_u32(host[:a]) == 0xDEADBEEF).all() and (_u32(host[b:]) == 0xDEADBEEF).all()
+
+
+def test_register_host_memory(par):
+    """par_register_host: page-lock caller-owned memory (e.g. a shared-memory frame)."""
+    W, H, L = 320, 200, 200
+    boxes, lights = par.scene_synthetic(W, H, L, n=300, n_lights=2)
+    buf = np.zeros((H, W), par.COLOR)
+    assert par.lib().par_register_host(buf.ctypes.data, buf.nbytes) == 0
+    try:
+        with par.Renderer(W, H, L) as r:
+            r.set_atlas()
+            r.set_scene(boxes)
+            want, _ = r.render(lights)
+            r.read_stripes(buf)
+            r.sync()
+        assert np.array_equal(_u32(buf), _u32(want))
+    finally:
+        par.lib().par_unregister_host(buf.ctypes.data)
+
+
 def test_determinism_and_rebuild_idempotence(par):
     W, H, L = 1920, 1080, 1080
     boxes, lights = par.scene_synthetic(W, H, L, n=10000, n_lights=8)
