@@ -219,16 +219,17 @@ def ours(args):
     h_frame = par.pinned_empty((H, W), par.COLOR) if rank == 0 else None
     t_hframe = torch.from_numpy(h_frame.view(np.uint8).reshape(-1)) if rank == 0 else None
 
-    # Frame exchange at N > 1.  "peer" (default): the shade kernel stores its finished stripes
-    # straight into every rank's raster frame through CUDA-IPC-mapped peer memory (NVLink), and a
-    # tiny all-reduce is the barrier.  "nccl": stripe-major staging + in-place all-gather + un-stripe.
+    # Frame exchange at N > 1.  "root" (default) / "peer": the shade kernel stores its finished
+    # stripes straight into rank 0's / every rank's raster frame through CUDA-IPC-mapped peer memory
+    # (NVLink); a tiny all-reduce is the barrier.  "nccl": stripe-major staging + in-place
+    # all-gather + un-stripe.
     exchange = "none" if world == 1 else args.exchange
     token = torch.zeros(1, dtype=torch.int32, device=dev)
-    if exchange == "peer":
+    if exchange in ("peer", "root"):
         try:
             handles = [None] * world
             dist.all_gather_object(handles, ren.peer_export())
-            for r in range(world):
+            for r in ([0] if exchange == "root" else range(world)):
                 if r != rank:
                     ren.peer_import(r, handles[r])
             ok = torch.ones(1, dtype=torch.int32, device=dev)
@@ -269,8 +270,8 @@ def ours(args):
     def render_and_gather():
         if world == 1:
             ren.render_device(lights, frame.data_ptr())
-        elif exchange == "peer":
-            ren.render_device_peers(lights)      # my stripes -> my frame and, in place, every peer's frame
+        elif exchange in ("peer", "root"):
+            ren.render_device_peers(lights)      # my stripes -> my frame and, in place, the imported peer frames
             dist.all_reduce(token)               # barrier: every rank's kernel (and its remote stores) is done
         else:
             ren.render_device_striped(lights, staging.data_ptr())  # my stripes, contiguous in staging
@@ -292,7 +293,7 @@ def ours(args):
             dist.all_reduce(token)               # the host frame is complete when every rank's DMA is
             return
         render_and_gather()
-        if exchange == "peer":
+        if exchange in ("peer", "root"):
             if rank == 0:
                 ren.read_frame(h_frame)          # D2H of the finished frame (it lives in the context's frame)
             dist.all_reduce(token)               # nobody starts overwriting frames before the reader is done
@@ -383,7 +384,7 @@ def ours(args):
         got_host = shared if shared is not None else h_frame
         if world == 1:
             got_dev = frame.cpu().numpy().view(par.COLOR).reshape(H, W)
-        elif exchange == "peer":
+        elif exchange in ("peer", "root"):
             got_dev = ren.read_frame()
             ren.sync()
         else:
@@ -450,7 +451,9 @@ def ours(args):
                    "n_lights": int(n_lights), "rays_per_frame": rays_frame,
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"interleaved 40-row stripes x{world}, frame exchange fused into the shade kernel "
-                                   "(peer-memory stores over NVLink + all-reduce barrier)" if exchange == "peer" else
+                                   "(peer-memory stores over NVLink + all-reduce barrier), frame complete on "
+                                   + ("rank 0 (gather-to-root)" if exchange == "root" else "every GPU (all-gather)")
+                                   if exchange in ("peer", "root") else
                                    f"interleaved 40-row stripes x{world} + in-place NCCL all-gather of the RGBA8 frame"),
                    "l2": "flushed between timed steps (256 MB fill)", "frames_per_s": round(1e3 * args.steps / ms, 2)},
         "e2e": {"value": round(e2e, 1), "unit": "Mrays/s", "ms_per_step": round(ms_e2e / args.steps, 4),
@@ -458,7 +461,7 @@ def ours(args):
                 "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4),
                 "readback": ("each rank DMAs its own stripes into one shared pinned host frame (N PCIe links)"
                              if shared is not None else "rank 0 / the one context copies the whole frame")},
-        "gpu_launches": ((4 if world == 1 or exchange == "peer" else 5) * args.steps) * world,
+        "gpu_launches": ((4 if world == 1 or exchange in ("peer", "root") else 5) * args.steps) * world,
         "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
                        "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},
         "roofline": roofline, "clocks": clocks, "frame_check": frame_check,
@@ -496,8 +499,10 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N>1 frame exchange: fused peer-memory stores (default) or NCCL all-gather")
+    ap.add_argument("--exchange", default="root", choices=["root", "peer", "nccl"],
+                    help="N>1 frame exchange, fused into the shade kernel as peer-memory stores: 'root' gathers the "
+                         "frame on rank 0 (default; SURVEY.md 8e gather-to-root), 'peer' completes it on every GPU; "
+                         "'nccl' = stripe-major staging + NCCL all-gather + un-stripe")
     ap.add_argument("--prewarm-ms", type=float, default=400.0, help="untimed GPU warm-up before the W warm-up steps")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

@@ -173,7 +173,11 @@ int par_unstripe_device(par_ctx* ctx, const void* d_staging, void* d_rgba);
  *   one process per GPU : par_peer_export (64-byte CUDA IPC handle of the own frame), exchange the
  *                         handles, par_peer_import(rank, handle) for every other rank;
  *   one process, N GPUs : par_peer_set(rank, par_device_frame(other ctx)) after enabling peer access.
- * par_render_device_peers renders asynchronously; the caller provides the cross-rank barrier. */
+ * par_render_device_peers stores into EVERY frame imported so far: import all other ranks for an
+ * all-gather (the frame complete on every GPU), or import only the root's frame on the other
+ * ranks (the root imports nothing) for a gather-to-root — 1/(N-1) of the NVLink traffic, the
+ * right choice when one GPU feeds the display / encoder.  It renders asynchronously; the caller
+ * provides the cross-rank barrier. */
 int par_peer_export(par_ctx* ctx, void* handle64);
 int par_peer_import(par_ctx* ctx, int rank, const void* handle64);
 int par_peer_set(par_ctx* ctx, int rank, void* d_peer_frame);
@@ -208,11 +212,15 @@ int par_grid_volume(const par_ctx* ctx);
  * summed over CTAs).  enable != 0 switches the instrumentation on and zeroes it. */
 int par_debug_phase_timing(par_ctx* ctx, int enable, uint64_t* out16);
 
-/* -- single-process multi-GPU: interleaved stripes + in-place ncclAllGather over NVLink ------ */
+/* -- single-process multi-GPU: interleaved stripes ------------------------------------------- */
 /* One par_ctx per device renders the tile rows t with t % n == i of the same scene (the scene
- * and grid are replicated) stripe-major into a staging frame; one in-place ncclAllGather and
- * an un-stripe copy complete the raster frame on every device.  NCCL is loaded lazily with
- * dlopen and only when n_devices > 1. */
+ * and grid are replicated).  Host consumer (out_rgba != NULL): every device DMAs its own stripes
+ * into out_rgba over its own PCIe link (par_read_stripes; pass par_alloc_host memory so the N
+ * copies run concurrently) — no GPU-to-GPU traffic.  Device consumer (out_rgba == NULL): the
+ * frame is completed on every device, by peer-memory stores fused into the shade kernel
+ * (par_peer_set) or, without peer access / with PAR_MULTI_EXCHANGE=nccl, by stripe-major
+ * staging + one in-place ncclAllGather + an un-stripe copy.  NCCL is loaded lazily with dlopen,
+ * only when that fallback is taken. */
 typedef struct par_multi par_multi;
 int par_multi_create(par_multi** out, const par_config* cfg, const int* devices, int n_devices);
 void par_multi_destroy(par_multi* m);
@@ -221,8 +229,8 @@ par_ctx* par_multi_context(par_multi* m, int i); /* device i's context (G-buffer
 int par_multi_set_atlas(par_multi* m, const par_sprite* sprites, int n_sprites,
                         const par_color* palette, int n_palette);
 int par_multi_set_scene(par_multi* m, const par_aabb* aabbs, const int32_t* sprite_ids, int n);
-/* Renders every stripe set, gathers, and reads the finished frame back from device 0 into out_rgba
- * (host, W*H; NULL = leave it in HBM, complete on every device).  Synchronous. */
+/* Renders every stripe set into out_rgba (host, W*H), or with out_rgba == NULL leaves the frame
+ * in HBM, complete on every device (par_device_frame(par_multi_context(m, i))).  Synchronous. */
 int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_color* out_rgba,
                      par_stats* stats);
 const char* par_multi_last_error(void);

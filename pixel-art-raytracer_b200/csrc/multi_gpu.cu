@@ -206,6 +206,14 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
         int rc = par_render_device(m->ctx[0], lights, n_lights, nullptr);
         if (rc != PAR_OK) return rc;
         if (out_rgba && (rc = par_read_stripes(m->ctx[0], out_rgba)) != PAR_OK) return rc;
+    } else if (out_rgba) {
+        // host consumer: no GPU-to-GPU exchange at all — every device renders its stripes into its
+        // own frame and ships them into the one host frame over its own PCIe link
+        for (int i = 0; i < m->n; i++) {
+            int rc = par_render_device(m->ctx[i], lights, n_lights, nullptr);
+            if (rc == PAR_OK) rc = par_read_stripes(m->ctx[i], out_rgba);
+            if (rc != PAR_OK) return rc;
+        }
     } else if (m->peer) {
         int prev = 0;
         cudaGetDevice(&prev);
@@ -214,8 +222,6 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
             if (rc != PAR_OK) return rc;
             cudaSetDevice(m->device[i]);
             cudaEventRecord(m->done[i], static_cast<cudaStream_t>(par_get_stream(m->ctx[i])));
-            // host frame: every device ships the stripes it rendered over its own PCIe link
-            if (out_rgba && (rc = par_read_stripes(m->ctx[i], out_rgba)) != PAR_OK) return rc;
         }
         for (int i = 0; i < m->n; i++) {  // a frame is complete once EVERY device has finished writing into it
             cudaSetDevice(m->device[i]);
@@ -244,7 +250,6 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
         for (int i = 0; i < m->n; i++) {  // staging -> raster frame on every device
             int rc = par_unstripe_device(m->ctx[i], m->staging[i], par_device_frame(m->ctx[i]));
             if (rc != PAR_OK) return rc;
-            if (out_rgba && (rc = par_read_stripes(m->ctx[i], out_rgba)) != PAR_OK) return rc;
         }
     }
     for (int i = 0; i < m->n; i++) {

@@ -714,8 +714,6 @@ int par_unregister_host(void* p) {
 
 int par_render_device_peers(par_ctx* c, const par_light* lights, int n_lights) {
     if (!c) return fail(PAR_ERR_INVALID_ARG, "par_render_device_peers: null context%s%s");
-    if (c->n_peers != c->d.stripe_n - 1)
-        return fail(PAR_ERR_STATE, "par_render_device_peers: import the frames of all other ranks first%s%s");
     return render_impl(c, lights, n_lights, c->d_frame, nullptr, false, true);
 }
 

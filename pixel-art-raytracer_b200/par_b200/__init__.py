@@ -374,7 +374,7 @@ class Renderer:
 
 
 class MultiRenderer:
-    """par_multi_*: one process, N GPUs, row bands + in-place ncclAllGather of the frame."""
+    """par_multi_*: one process, N GPUs, interleaved stripes (see par.h)."""
 
     def __init__(self, W, H, L, devices):
         self.W, self.H, self.L = W, H, L
@@ -423,3 +423,18 @@ class MultiRenderer:
         st = Stats()
         self._check(lib().par_multi_render(self._h, _p(lights), len(lights), _p(rgba), C.byref(st)))
         return rgba, st.as_dict()
+
+    def render_resident(self, lights):
+        """Device consumer: leave the finished frame in HBM, complete on every device."""
+        lights = np.ascontiguousarray(lights, LIGHT)
+        st = Stats()
+        self._check(lib().par_multi_render(self._h, _p(lights), len(lights), None, C.byref(st)))
+        return st.as_dict()
+
+    def device_frame_copy(self, i) -> np.ndarray:
+        """Synchronous copy of device i's raster frame (after render_resident: the whole frame)."""
+        ctx = lib().par_multi_context(self._h, i)
+        out = np.zeros((self.H, self.W), COLOR)
+        _check(lib().par_read_frame(ctx, _p(out)))
+        _check(lib().par_sync(ctx))
+        return out

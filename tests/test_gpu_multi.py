@@ -40,22 +40,30 @@ def test_multi_equals_single(par, n):
     assert st["rays"] == W * H * 7
 
 
-def test_multi_nccl_fallback_path(par, monkeypatch):
-    """The NCCL all-gather path of par_multi_* (used when peer access is unavailable)."""
-    if _n_gpus() < 2:
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
+def test_multi_device_resident_frame_complete_everywhere(par, monkeypatch, exchange):
+    """par_multi_render(out = NULL): the frame is completed in HBM on EVERY device — by the
+    peer-memory stores fused into the shade kernel, or by the NCCL all-gather fallback."""
+    n = min(_n_gpus(), 4)
+    if n < 2:
         pytest.skip("needs 2 GPUs")
-    monkeypatch.setenv("PAR_MULTI_EXCHANGE", "nccl")
+    if exchange == "nccl":
+        monkeypatch.setenv("PAR_MULTI_EXCHANGE", "nccl")
     W, H, L = 1280, 720, 720
     boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
     with par.Renderer(W, H, L) as r:
         r.set_atlas()
         r.set_scene(boxes)
         one, _ = r.render(lights)
-    with par.MultiRenderer(W, H, L, [0, 1]) as m:
+    with par.MultiRenderer(W, H, L, list(range(n))) as m:
         m.set_atlas()
         m.set_scene(boxes)
-        many, _ = m.render(lights)
-    assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
+        for _ in range(2):  # twice: the second frame overwrites a complete one
+            m.render_resident(lights)
+        for i in range(n):
+            assert np.array_equal(one.view(np.uint32), m.device_frame_copy(i).view(np.uint32)), f"device {i}"
+        host, _ = m.render(lights)  # host consumer afterwards: parallel stripe readback
+    assert np.array_equal(one.view(np.uint32), host.view(np.uint32))
 
 
 def test_fused_peer_exchange_two_contexts(par):
@@ -85,6 +93,36 @@ def test_fused_peer_exchange_two_contexts(par):
         b.sync()
     assert np.array_equal(one.view(np.uint32), fa.view(np.uint32))
     assert np.array_equal(one.view(np.uint32), fb.view(np.uint32))
+
+
+def test_fused_gather_to_root(par):
+    """Only rank 0's frame is imported (by rank 1): the frame completes on rank 0 alone."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H, L = 1280, 720, 720
+    boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        one, _ = r.render(lights)
+    with par.Renderer(W, H, L, device=0, stripe_count=2, stripe_index=0) as a, \
+            par.Renderer(W, H, L, device=1, stripe_count=2, stripe_index=1) as b:
+        b.peer_set(0, a.device_frame())
+        for r in (a, b):
+            r.set_atlas()
+            r.set_scene(boxes)
+            r.render_device_peers(lights)
+        a.sync()
+        b.sync()
+        fa, fb = a.read_frame(), b.read_frame()
+        a.sync()
+        b.sync()
+    assert np.array_equal(one.view(np.uint32), fa.view(np.uint32))
+    own_b = np.zeros(H, bool)
+    for t in range(1, H // 40, 2):
+        own_b[t * 40:t * 40 + 40] = True
+    assert np.array_equal(one.view(np.uint32)[own_b], fb.view(np.uint32)[own_b])
+    assert not fb.view(np.uint32)[~own_b].any()
 
 
 def test_multi_single_device_is_plain(par):
