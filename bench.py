@@ -300,6 +300,34 @@ def ours(args):
         elif rank == 0:
             t_hframe.copy_(frame, non_blocking=True)  # D2H of the gathered frame
 
+    def timed_pipelined(steps, warmup):
+        """e2e at N = 1 through par_submit_frame / par_wait_frame: two frames in flight, every step
+        uploads the scene from pinned memory and reads its frame back into pinned memory; the timed
+        region starts with an empty pipeline and ends when the last frame is complete on the host."""
+        h_out = [h_frame, par.pinned_empty((H, W), par.COLOR)]
+        with torch.cuda.stream(stream):
+            for i in range(warmup + 1):
+                if i < warmup:
+                    ren.submit_frame(h_boxes, lights, h_out[i & 1])
+                if i:
+                    ren.wait_frame()
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            t0 = time.perf_counter()
+            for i in range(steps + 1):
+                if i < steps:
+                    flush.fill_(1)               # L2 flush between iterations (inside the timed region here)
+                    ren.submit_frame(h_boxes, lights, h_out[i & 1])
+                if i:
+                    ren.wait_frame()
+            b.record(stream)
+            barrier()
+            t1 = time.perf_counter()
+        if (steps - 1) & 1:                      # the check below looks at h_frame
+            h_frame[:] = h_out[1]
+        return a.elapsed_time(b), t0, t1
+
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -357,6 +385,9 @@ def ours(args):
     st = ren.stats()                            # per-kernel CUDA-event times of the last step
     trace("resident timing done")
     ms_e2e, _, t1 = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+    ms_e2e_sync = ms_e2e
+    if world == 1:
+        ms_e2e, _, t1 = timed_pipelined(args.steps, max(2, args.warmup // 2))
     trace("e2e timing done")
     clocks = sampler.stop(t_load0 - args.prewarm_ms / 1e3, t1) if sampler else None  # pre-warm + timed regions: under load
 
@@ -460,8 +491,14 @@ def ours(args):
                 "frames_per_s": round(1e3 * args.steps / ms_e2e, 2),
                 "h2d_bytes_per_step": int(h_boxes.nbytes) * world, "d2h_bytes_per_step": int(H * W * 4),
                 "readback": ("each rank DMAs its own stripes into one shared pinned host frame (N PCIe links)"
-                             if shared is not None else "rank 0 / the one context copies the whole frame")},
-        "gpu_launches": ((4 if world == 1 or exchange in ("peer", "root") else 5) * args.steps) * world,
+                             if shared is not None else "rank 0 / the one context copies the whole frame"),
+                "api": ("par_submit_frame / par_wait_frame, two frames in flight (readback of frame k beside upload "
+                        "and kernels of frame k+1); timed from an empty pipeline to the last frame complete on the "
+                        "host, L2 flush inside the timed region" if world == 1 else
+                        "par_set_scene + par_render_device + par_read_stripes per rank, barrier per step"),
+                "sync_call_ms": round(ms_e2e_sync / args.steps, 4) if world == 1 else None,
+                "sync_call": "par_set_scene + par_render (blocking drop-in call) per step" if world == 1 else None},
+        "gpu_launches": ((6 if world == 1 or exchange in ("peer", "root") else 7) * args.steps) * world,
         "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
                        "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},
         "roofline": roofline, "clocks": clocks, "frame_check": frame_check,

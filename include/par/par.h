@@ -107,7 +107,10 @@ typedef struct par_stats {
     uint64_t rays;         /* reference-equivalent rays: rows*W*(1+n_lights)           */
     uint64_t slab_tests;   /* reserved (0)                                              */
     float ms_walks;        /* shadow-walk kernel (one warp per tile x z-group x light)  */
-    int32_t reserved[3];
+    float ms_readback;     /* par_wait_frame only: kernels done -> frame complete on the host
+                            * (queueing behind the previous frame's copy + the D2H itself);
+                            * ms_total is submit -> complete, the per-kernel times stay 0 */
+    int32_t reserved[2];
 } par_stats;
 
 typedef struct par_ctx par_ctx;
@@ -192,6 +195,19 @@ int par_read_frame(par_ctx* ctx, par_color* out_rgba);
  * N PCIe links in parallel and no GPU-to-GPU exchange is needed for a host-side consumer
  * (the SDL texture upload of alternative.cpp:786-788 reads host memory). */
 int par_read_stripes(par_ctx* ctx, par_color* host_frame);
+/* Pipelined frames — the throughput form of par_set_scene + par_render for a host that produces
+ * a scene and consumes a frame every iteration (the reference's loop, alternative.cpp:641-788).
+ * par_submit_frame enqueues upload, grid build, both kernels and the readback of the rows this
+ * context owns into out_rgba (a full W*H frame) and returns; at most two frames are in flight.
+ * par_wait_frame blocks until the OLDEST frame in flight is complete in its out_rgba (status
+ * and stats are that frame's; ms_total = submit to completion).  The readback of frame k runs
+ * on a second stream beside the upload and kernels of frame k+1 (PCIe is full duplex), so a
+ * frame costs max(readback, upload + kernels) instead of their sum.  aabbs / sprite_ids /
+ * out_rgba should be page-locked (par_alloc_host) and must stay untouched until that frame has
+ * been waited for — a moving scene alternates two AABB arrays the way it alternates two frames. */
+int par_submit_frame(par_ctx* ctx, const par_aabb* aabbs, const int32_t* sprite_ids, int n,
+                     const par_light* lights, int n_lights, par_color* out_rgba);
+int par_wait_frame(par_ctx* ctx, par_stats* stats);
 /* Page-lock / unlock host memory the caller already owns (e.g. a shared-memory frame), so that
  * copies into it are asynchronous DMA. */
 int par_register_host(void* p, size_t bytes);

@@ -127,6 +127,12 @@ struct par_ctx {
     uchar4* peer_frame[8] = {};
     bool peer_is_ipc[8] = {};
     int n_peers = 0;  // entries of peer_frame in use (own rank's entry stays NULL)
+    // pipelined frames (par_submit_frame / par_wait_frame): two slots, each with its own device frame
+    uchar4* d_frame_alt = nullptr;  // slot 1's frame, allocated on first use (slot 0 uses d_frame)
+    cudaEvent_t ev_slot_begin[2] = {}, ev_slot_kernels[2] = {}, ev_slot_done[2] = {};
+    int slots_in_flight = 0, slot_oldest = 0, slot_next = 0, slot_lights[2] = {};
+    bool capturing = false;            // a pipelined frame is being captured into frame_exec
+    cudaGraphExec_t frame_exec = nullptr;  // upload + build + kernels of one pipelined frame as ONE graph launch
     float last_kernel_ms = 0.f;  // primary + shade of the previous par_render (pipelining heuristic)
     int readback_chunks = 3;  // row chunks of the pipelined readback (PAR_READBACK_CHUNKS overrides)
     int debug_flags = 0;  // from the PAR_DEBUG_FLAGS environment variable (developer A/B switches)
@@ -147,28 +153,46 @@ struct DeviceGuard {
     }
 };
 
-int run_loader(par_ctx* c) {
+// Timing events of the synchronous calls.  While a pipelined frame is captured into a CUDA graph
+// they are skipped: an event recorded by a graph node can no longer be queried from the host.
+cudaError_t record_timing(par_ctx* c, cudaEvent_t ev) {
+    return c->capturing ? cudaSuccess : cudaEventRecord(ev, c->stream);
+}
+
+int run_loader(par_ctx* c, LoaderCounters* slot_ctr = nullptr) {
     c->launches_build = 0;
-    PAR_CUDA(cudaEventRecord(c->ev_build0, c->stream));
+    PAR_CUDA(record_timing(c, c->ev_build0));
     PAR_CUDA(launch_scene_loader(c->d_raw, c->has_sprite_ids ? c->d_sprite_ids : nullptr,
                                  c->n_entities, c->n_sprites, c->d, c->d_boxes, c->d_cnt, c->d_ids,
-                                 c->d_occ4, c->d_survivors, c->d_ctr, c->stream, &c->launches_build));
-    PAR_CUDA(cudaEventRecord(c->ev_build1, c->stream));
-    PAR_CUDA(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(LoaderCounters), cudaMemcpyDeviceToHost,
-                             c->stream));
-    c->build_timed = true;
+                                 c->d_occ4, c->d_survivors, c->d_ctr, c->h_ctr, slot_ctr, c->stream,
+                                 &c->launches_build));
+    PAR_CUDA(record_timing(c, c->ev_build1));
+    c->build_timed = !c->capturing;
     c->scene_set = true;
     c->frame_valid = false;
     return PAR_OK;
 }
 
-int check_scene_flag(par_ctx* c) {
-    if (c->h_ctr->bad_scene)
-        return fail(PAR_ERR_BAD_SCENE,
-                    "scene has an AABB with extent.x outside [0,20], extent.y+extent.z outside "
-                    "[0,40] or a sprite id outside the atlas (would index outside the 20x40 "
-                    "sprite, alternative.cpp:330)%s%s");
-    return PAR_OK;
+int bad_scene_error() {
+    return fail(PAR_ERR_BAD_SCENE,
+                "scene has an AABB with extent.x outside [0,20], extent.y+extent.z outside "
+                "[0,40] or a sprite id outside the atlas (would index outside the 20x40 "
+                "sprite, alternative.cpp:330)%s%s");
+}
+
+int check_scene_flag(par_ctx* c) { return c->h_ctr->bad_scene ? bad_scene_error() : PAR_OK; }
+
+// Image rows the context renders (its band, restricted to its stripes).
+uint64_t owned_row_count(const par_ctx* c) {
+    uint64_t rows = 0;
+    int first, count;
+    owned_tile_rows(c->d, first, count);
+    for (int t = first, q = 0; q < count; q++, t += c->d.stripe_n) {
+        const int a = t * kBin > c->d.row0 ? t * kBin : c->d.row0;
+        const int b = (t + 1) * kBin < c->d.row1 ? (t + 1) * kBin : c->d.row1;
+        rows += (uint64_t)(b - a);
+    }
+    return rows;
 }
 
 }  // namespace
@@ -243,8 +267,13 @@ int par_create(par_ctx** out, const par_config* cfg) {
         PAR_CUDA(cudaMalloc(&c->d_ids, sizeof(int) * (size_t)d.V * kSlots));
         PAR_CUDA(cudaMalloc(&c->d_occ4, sizeof(unsigned) * (((size_t)d.V + 7) / 8)));
         PAR_CUDA(cudaMalloc(&c->d_ctr, sizeof(LoaderCounters)));
-        PAR_CUDA(cudaMallocHost(&c->h_ctr, sizeof(LoaderCounters)));
-        memset(c->h_ctr, 0, sizeof(LoaderCounters));
+        PAR_CUDA(cudaMallocHost(&c->h_ctr, 3 * sizeof(LoaderCounters)));  // [0] latest build, [1 + slot] pipelined frames
+        memset(c->h_ctr, 0, 3 * sizeof(LoaderCounters));
+        for (int k = 0; k < 2; k++) {
+            PAR_CUDA(cudaEventCreate(&c->ev_slot_begin[k]));
+            PAR_CUDA(cudaEventCreate(&c->ev_slot_kernels[k]));
+            PAR_CUDA(cudaEventCreate(&c->ev_slot_done[k]));
+        }
         const size_t tiles = (size_t)d.HW * d.HH;
         PAR_CUDA(cudaMalloc(&c->d_tile_ngroups, sizeof(int) * tiles));
         PAR_CUDA(cudaMalloc(&c->d_groups, sizeof(GroupMeta) * tiles * kMaxGroups));
@@ -269,6 +298,7 @@ void par_destroy(par_ctx* c) {
     if (!c) return;
     DeviceGuard guard(c->cfg.device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     cudaFree(c->d_raw);
     cudaFree(c->d_boxes);
     cudaFree(c->d_sprite_ids);
@@ -291,6 +321,13 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_pool_cursor);
     cudaFree(c->d_gbuf);
     cudaFree(c->d_frame);
+    cudaFree(c->d_frame_alt);
+    if (c->frame_exec) cudaGraphExecDestroy(c->frame_exec);
+    for (int k = 0; k < 2; k++) {
+        if (c->ev_slot_begin[k]) cudaEventDestroy(c->ev_slot_begin[k]);
+        if (c->ev_slot_kernels[k]) cudaEventDestroy(c->ev_slot_kernels[k]);
+        if (c->ev_slot_done[k]) cudaEventDestroy(c->ev_slot_done[k]);
+    }
     cudaFree(c->d_expanded);
     cudaFree(c->d_texel);
     cudaFree(c->d_phase_cycles);
@@ -402,26 +439,36 @@ int par_set_atlas(par_ctx* c, const par_sprite* sprites, int n_sprites, const pa
     return rc;
 }
 
-int par_set_scene(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n) {
+// Room for n entities in the scene buffers (synchronises the stream when it has to reallocate).
+static int reserve_entities(par_ctx* c, int n) {
+    if (n <= c->cap_entities) return PAR_OK;
+    PAR_CUDA(cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_raw);
+    cudaFree(c->d_boxes);
+    cudaFree(c->d_sprite_ids);
+    cudaFree(c->d_survivors);
+    c->d_raw = c->d_boxes = nullptr;
+    c->d_sprite_ids = c->d_survivors = nullptr;
+    c->cap_entities = 0;
+    size_t cap = (size_t)n + (size_t)n / 8 + 64;
+    PAR_CUDA(cudaMalloc(&c->d_raw, sizeof(int4) * cap));
+    PAR_CUDA(cudaMalloc(&c->d_boxes, sizeof(int4) * cap));
+    PAR_CUDA(cudaMalloc(&c->d_sprite_ids, sizeof(int) * cap));
+    PAR_CUDA(cudaMalloc(&c->d_survivors, sizeof(int) * cap));
+    c->cap_entities = (int)cap;
+    return PAR_OK;
+}
+
+static int set_scene_impl(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n,
+                          LoaderCounters* slot_ctr) {
     if (!c || n < 0 || n > (1 << 26) || (n > 0 && !aabbs))
         return fail(PAR_ERR_INVALID_ARG, "par_set_scene: bad argument (at most 2^26 entities)%s%s");
     if (c->n_sprites == 0) return fail(PAR_ERR_STATE, "par_set_scene: call par_set_atlas first%s%s");
     DeviceGuard guard(c->cfg.device);
     if (n > c->cap_entities) {
-        PAR_CUDA(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_raw);
-        cudaFree(c->d_boxes);
-        cudaFree(c->d_sprite_ids);
-        cudaFree(c->d_survivors);
-        c->d_raw = c->d_boxes = nullptr;
-        c->d_sprite_ids = c->d_survivors = nullptr;
-        c->cap_entities = 0;
-        size_t cap = (size_t)n + (size_t)n / 8 + 64;
-        PAR_CUDA(cudaMalloc(&c->d_raw, sizeof(int4) * cap));
-        PAR_CUDA(cudaMalloc(&c->d_boxes, sizeof(int4) * cap));
-        PAR_CUDA(cudaMalloc(&c->d_sprite_ids, sizeof(int) * cap));
-        PAR_CUDA(cudaMalloc(&c->d_survivors, sizeof(int) * cap));
-        c->cap_entities = (int)cap;
+        if (c->capturing) return fail(PAR_ERR_STATE, "par_submit_frame: internal: capacity must grow before the capture%s%s");
+        int rc = reserve_entities(c, n);
+        if (rc != PAR_OK) return rc;
     }
     c->n_entities = n;
     c->has_sprite_ids = sprite_ids != nullptr;
@@ -432,7 +479,11 @@ int par_set_scene(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, 
             PAR_CUDA(cudaMemcpyAsync(c->d_sprite_ids, sprite_ids, sizeof(int) * (size_t)n,
                                      cudaMemcpyHostToDevice, c->stream));
     }
-    return run_loader(c);
+    return run_loader(c, slot_ctr);
+}
+
+int par_set_scene(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n) {
+    return set_scene_impl(c, aabbs, sprite_ids, n, nullptr);
 }
 
 int par_rebuild_grid(par_ctx* c) {
@@ -447,7 +498,9 @@ int par_rebuild_grid(par_ctx* c) {
 // rendering of chunk k+1 on a second stream — at 4K the 33 MB readback takes about as long as
 // the kernels, so the drop-in call is roughly max(render, copy) instead of their sum.
 static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4* d_out, par_color* host_out,
-                       bool striped_out = false, bool to_peers = false) {
+                       bool striped_out = false, bool to_peers = false, bool pipelined = false) {
+    if (c && c->slots_in_flight && !pipelined)
+        return fail(PAR_ERR_STATE, "par_render: pipelined frames in flight, call par_wait_frame first%s%s");
     if (!c || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
         return fail(PAR_ERR_INVALID_ARG, "par_render: bad argument (at most 64 lights)%s%s");
     if (!c->scene_set || c->n_sprites == 0)
@@ -544,7 +597,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
         const float copy_ms = (float)(d.row1 - d.row0) * d.W * 4.f / 50e6f;  // ~50 GB/s PCIe gen5
         if (pinned && c->last_kernel_ms > 0.f && c->last_kernel_ms < 2.5f * copy_ms) n_chunks = c->readback_chunks;
     }
-    PAR_CUDA(cudaEventRecord(c->ev_f0, c->stream));
+    PAR_CUDA(record_timing(c, c->ev_f0));
     for (int k = 0; k < n_chunks; k++) {
         const int ta = tile0 + (tile1 - tile0) * k / n_chunks, tb = tile0 + (tile1 - tile0) * (k + 1) / n_chunks;
         const int ra = ta * kBin > d.row0 ? ta * kBin : d.row0, rb = tb * kBin < d.row1 ? tb * kBin : d.row1;
@@ -553,13 +606,13 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
         int first_owned, n_owned;
         owned_tile_rows(pp.d, first_owned, n_owned);
         pp.tile_row_first = sp.tile_row_first = wp.tile_row_first = first_owned;
-        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][0], c->stream));
+        PAR_CUDA(record_timing(c, c->ev_chunk[k][0]));
         PAR_CUDA(launch_primary(pp, c->stream));
-        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][1], c->stream));
+        PAR_CUDA(record_timing(c, c->ev_chunk[k][1]));
         if (use_walks) PAR_CUDA(launch_walks(wp, c->stream));
-        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][2], c->stream));
+        PAR_CUDA(record_timing(c, c->ev_chunk[k][2]));
         PAR_CUDA(launch_shade(sp, c->stream));
-        PAR_CUDA(cudaEventRecord(c->ev_chunk[k][3], c->stream));
+        PAR_CUDA(record_timing(c, c->ev_chunk[k][3]));
         if (host_out && d.stripe_n == 1) {
             const size_t first = (size_t)ra * d.W, count = (size_t)(rb - ra) * d.W;
             cudaStream_t cs = n_chunks > 1 ? c->copy_stream : c->stream;
@@ -575,7 +628,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
             }
         }
     }
-    PAR_CUDA(cudaEventRecord(c->ev_f2, c->stream));
+    PAR_CUDA(record_timing(c, c->ev_f2));
     if (host_out && n_chunks > 1) {  // make the context's stream cover the copies too
         PAR_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
         PAR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
@@ -584,7 +637,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     c->launches_frame = (use_walks ? 3 : 2) * n_chunks;
     c->last_n_lights = n_lights;
     c->frame_valid = true;
-    c->frame_timed = true;
+    c->frame_timed = !c->capturing;
     return PAR_OK;
 }
 
@@ -663,9 +716,8 @@ int par_read_frame(par_ctx* c, par_color* out_rgba) {
     return PAR_OK;
 }
 
-int par_read_stripes(par_ctx* c, par_color* host_frame) {
-    if (!c || !host_frame) return fail(PAR_ERR_INVALID_ARG, "par_read_stripes: null argument%s%s");
-    DeviceGuard guard(c->cfg.device);
+// D2H of the rows the context owns, from a raster frame in HBM into the same rows of a host frame.
+static int enqueue_owned_rows_d2h(par_ctx* c, const uchar4* d_src, par_color* host_frame, cudaStream_t st) {
     const ViewDims& d = c->d;
     const size_t row_bytes = sizeof(par_color) * (size_t)d.W;
     int first, count;
@@ -674,27 +726,139 @@ int par_read_stripes(par_ctx* c, par_color* host_frame) {
     const int n = d.stripe_n > 1 ? d.stripe_n : 1;
     const int last = first + (count - 1) * n;
     const bool whole_tiles = first * kBin >= d.row0 && (last + 1) * kBin <= d.row1;
+    char* dst = reinterpret_cast<char*>(host_frame);
+    const char* src = reinterpret_cast<const char*>(d_src);
     if (n == 1) {  // a band (or the whole frame): one contiguous block
-        PAR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host_frame) + d.row0 * row_bytes,
-                                 reinterpret_cast<const char*>(c->d_frame) + d.row0 * row_bytes,
-                                 row_bytes * (size_t)(d.row1 - d.row0), cudaMemcpyDeviceToHost, c->stream));
+        PAR_CUDA(cudaMemcpyAsync(dst + d.row0 * row_bytes, src + d.row0 * row_bytes,
+                                 row_bytes * (size_t)(d.row1 - d.row0), cudaMemcpyDeviceToHost, st));
         return PAR_OK;
     }
     if (whole_tiles) {  // the owned stripes lie at a regular pitch: one strided DMA
         const size_t pitch = row_bytes * kBin * n, off = (size_t)first * kBin * row_bytes;
-        PAR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(host_frame) + off, pitch,
-                                   reinterpret_cast<const char*>(c->d_frame) + off, pitch, row_bytes * kBin, count,
-                                   cudaMemcpyDeviceToHost, c->stream));
+        PAR_CUDA(cudaMemcpy2DAsync(dst + off, pitch, src + off, pitch, row_bytes * kBin, count,
+                                   cudaMemcpyDeviceToHost, st));
         return PAR_OK;
     }
     for (int t = first; t <= last; t += n) {  // band edges inside a tile row: one copy per clipped stripe
         const int r0 = std::max(t * kBin, d.row0), r1 = std::min((t + 1) * kBin, d.row1);
         if (r1 <= r0) continue;
-        PAR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host_frame) + r0 * row_bytes,
-                                 reinterpret_cast<const char*>(c->d_frame) + r0 * row_bytes,
-                                 row_bytes * (size_t)(r1 - r0), cudaMemcpyDeviceToHost, c->stream));
+        PAR_CUDA(cudaMemcpyAsync(dst + r0 * row_bytes, src + r0 * row_bytes, row_bytes * (size_t)(r1 - r0),
+                                 cudaMemcpyDeviceToHost, st));
     }
     return PAR_OK;
+}
+
+int par_read_stripes(par_ctx* c, par_color* host_frame) {
+    if (!c || !host_frame) return fail(PAR_ERR_INVALID_ARG, "par_read_stripes: null argument%s%s");
+    DeviceGuard guard(c->cfg.device);
+    return enqueue_owned_rows_d2h(c, c->d_frame, host_frame, c->stream);
+}
+
+// ---- pipelined frames ------------------------------------------------------------------------------
+// Main stream:  [H2D scene k+1][loader][primary][shade] ...      copy stream:  [D2H frame k]
+// PCIe is full duplex and the copy engines run beside the SMs, so in steady state a frame costs
+// max(D2H, H2D + kernels) instead of their sum.  Two slots: each has its own device frame (the
+// copy of frame k reads slot k&1 while frame k+1 is shaded into the other) and its own copy of
+// the loader's counters.
+int par_submit_frame(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n, const par_light* lights,
+                     int n_lights, par_color* out_rgba) {
+    if (!c || !out_rgba) return fail(PAR_ERR_INVALID_ARG, "par_submit_frame: null argument%s%s");
+    if (n < 0 || n > (1 << 26) || (n > 0 && !aabbs) || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
+        return fail(PAR_ERR_INVALID_ARG, "par_submit_frame: bad argument (at most 2^26 entities, 64 lights)%s%s");
+    if (c->n_sprites == 0) return fail(PAR_ERR_STATE, "par_submit_frame: call par_set_atlas first%s%s");
+    if (c->slots_in_flight == 2)
+        return fail(PAR_ERR_STATE, "par_submit_frame: two frames in flight, call par_wait_frame first%s%s");
+    DeviceGuard guard(c->cfg.device);
+    const int slot = c->slot_next;
+    if (slot == 1 && !c->d_frame_alt) {
+        const size_t px = (size_t)c->d.W * c->d.H;
+        PAR_CUDA(cudaMalloc(&c->d_frame_alt, sizeof(uchar4) * px));
+        PAR_CUDA(cudaMemsetAsync(c->d_frame_alt, 0, sizeof(uchar4) * px, c->stream));
+    }
+    uchar4* d_out = slot ? c->d_frame_alt : c->d_frame;
+    PAR_CUDA(cudaEventRecord(c->ev_slot_begin[slot], c->stream));
+    // Upload, grid build and both kernels go to the GPU as ONE graph launch: while the previous
+    // frame's readback saturates PCIe, every separate launch costs ~25 us of command fetch latency
+    // (measured: 0.36 ms of kernels stretch to 0.66 ms beside a running D2H).  The graph is
+    // re-captured each frame (pointers, light values and grid sizes change) and the executable is
+    // updated in place.  Needs page-locked inputs (a pageable copy cannot be captured).
+    bool use_graph = !(c->debug_flags & (8 | 16)) && c->stream != nullptr && c->stream != cudaStreamLegacy &&
+                     c->stream != cudaStreamPerThread;
+    if (use_graph) {
+        cudaPointerAttributes attr;
+        use_graph = n == 0 || (cudaPointerGetAttributes(&attr, aabbs) == cudaSuccess && attr.type == cudaMemoryTypeHost);
+        if (use_graph && sprite_ids)
+            use_graph = cudaPointerGetAttributes(&attr, sprite_ids) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+    }
+    int rc = PAR_OK;
+    if (use_graph) {
+        if ((rc = reserve_entities(c, n)) != PAR_OK) return rc;  // may reallocate: not allowed inside a capture
+        PAR_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+        c->capturing = true;
+        rc = set_scene_impl(c, aabbs, sprite_ids, n, &c->h_ctr[1 + slot]);
+        if (rc == PAR_OK) rc = render_impl(c, lights, n_lights, d_out, nullptr, false, false, true);
+        c->capturing = false;
+        cudaGraph_t graph = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+        if (rc != PAR_OK) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc;
+        }
+        PAR_CUDA(ce);
+        if (c->frame_exec) {
+            cudaGraphExecUpdateResultInfo info;
+            if (cudaGraphExecUpdate(c->frame_exec, graph, &info) != cudaSuccess) {  // topology changed: rebuild
+                cudaGetLastError();
+                cudaGraphExecDestroy(c->frame_exec);
+                c->frame_exec = nullptr;
+            }
+        }
+        if (!c->frame_exec) {
+            ce = cudaGraphInstantiate(&c->frame_exec, graph, 0);
+            if (ce != cudaSuccess) {
+                cudaGraphDestroy(graph);
+                PAR_CUDA(ce);
+            }
+        }
+        cudaGraphDestroy(graph);
+        PAR_CUDA(cudaGraphLaunch(c->frame_exec, c->stream));
+    } else {
+        rc = set_scene_impl(c, aabbs, sprite_ids, n, &c->h_ctr[1 + slot]);
+        if (rc != PAR_OK) return rc;
+        if ((rc = render_impl(c, lights, n_lights, d_out, nullptr, false, false, true)) != PAR_OK) return rc;
+    }
+    PAR_CUDA(cudaEventRecord(c->ev_slot_kernels[slot], c->stream));
+    PAR_CUDA(cudaStreamWaitEvent(c->copy_stream, c->ev_slot_kernels[slot], 0));
+    if ((rc = enqueue_owned_rows_d2h(c, d_out, out_rgba, c->copy_stream)) != PAR_OK) return rc;
+    PAR_CUDA(cudaEventRecord(c->ev_slot_done[slot], c->copy_stream));
+    c->slot_lights[slot] = n_lights;
+    c->slot_next = slot ^ 1;
+    c->slots_in_flight++;
+    return PAR_OK;
+}
+
+int par_wait_frame(par_ctx* c, par_stats* stats) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_wait_frame: null context%s%s");
+    if (c->slots_in_flight == 0) return fail(PAR_ERR_STATE, "par_wait_frame: no frame in flight%s%s");
+    DeviceGuard guard(c->cfg.device);
+    const int slot = c->slot_oldest;
+    c->slot_oldest = slot ^ 1;
+    c->slots_in_flight--;
+    PAR_CUDA(cudaEventSynchronize(c->ev_slot_done[slot]));
+    const LoaderCounters& lc = c->h_ctr[1 + slot];
+    if (stats) {
+        memset(stats, 0, sizeof *stats);
+        PAR_CUDA(cudaEventElapsedTime(&stats->ms_total, c->ev_slot_begin[slot], c->ev_slot_done[slot]));
+        PAR_CUDA(cudaEventElapsedTime(&stats->ms_readback, c->ev_slot_kernels[slot], c->ev_slot_done[slot]));
+        stats->kernel_launches = c->launches_build + c->launches_frame;
+        stats->n_entities = c->n_entities;
+        stats->n_survivors = lc.n_survivors;
+        stats->n_inserts = lc.n_inserts;
+        stats->rays = owned_row_count(c) * c->d.W * (1 + (uint64_t)c->slot_lights[slot]);
+    }
+    return lc.bad_scene ? bad_scene_error() : PAR_OK;
 }
 
 int par_register_host(void* p, size_t bytes) {
@@ -772,17 +936,7 @@ int par_get_stats(par_ctx* c, par_stats* st) {
     st->n_entities = c->n_entities;
     st->n_survivors = c->h_ctr->n_survivors;
     st->n_inserts = c->h_ctr->n_inserts;
-    uint64_t rows = 0;
-    {
-        int first, count;
-        owned_tile_rows(c->d, first, count);
-        for (int t = first, q = 0; q < count; q++, t += c->d.stripe_n) {
-            const int a = t * kBin > c->d.row0 ? t * kBin : c->d.row0;
-            const int b = (t + 1) * kBin < c->d.row1 ? (t + 1) * kBin : c->d.row1;
-            rows += (uint64_t)(b - a);
-        }
-    }
-    st->rays = rows * c->d.W * (1 + (uint64_t)c->last_n_lights);
+    st->rays = owned_row_count(c) * c->d.W * (1 + (uint64_t)c->last_n_lights);
     return PAR_OK;
 }
 

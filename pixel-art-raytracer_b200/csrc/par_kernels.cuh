@@ -15,6 +15,7 @@ struct LoaderCounters {
 cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,
                                 const ViewDims& d, int4* boxes, int* cnt, int* ids,
                                 unsigned* occ4, int* survivors, LoaderCounters* ctr,
+                                LoaderCounters* host_a, LoaderCounters* host_b,
                                 cudaStream_t s, int* launches);
 
 // ---- per-tile shadow-walk work descriptors (primary -> walks -> shade) ----

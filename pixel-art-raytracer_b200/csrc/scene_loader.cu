@@ -16,6 +16,8 @@
 //                       4-bit-per-bin table (read by the shadow walk: one small load answers
 //                       "occupied?" and "how many?").
 // Readers map the reference's slot s to ids[bin*8 + (cnt&7) - 1 - s].
+#include <algorithm>
+
 #include "par_kernels.cuh"
 
 namespace par {
@@ -72,16 +74,40 @@ k_occupancy(const int* __restrict__ survivors, const int4* __restrict__ boxes, V
             }
 }
 
-// Host-side launcher (called from par_api.cu).
+// Clears the grid for a new build in ONE launch: insert totals 0, slots -1, occupancy 0, counters 0.
+// (cudaMemsetAsync may be served by a copy engine, where it would queue behind the previous
+// frame's readback when frames are pipelined — and four memset nodes cost more than one kernel.)
+__global__ void __launch_bounds__(256)
+k_clear_grid(int* __restrict__ cnt, int* __restrict__ ids, unsigned* __restrict__ occ4,
+             LoaderCounters* __restrict__ ctr, int V) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    int4* ids4 = reinterpret_cast<int4*>(ids);  // kSlots = 8 ints per bin = 2 int4
+    for (size_t i = tid; i < (size_t)V * (kSlots / 4); i += nthr) ids4[i] = make_int4(-1, -1, -1, -1);
+    for (size_t i = tid; i < (size_t)V; i += nthr) cnt[i] = 0;
+    for (size_t i = tid; i < ((size_t)V + 7) / 8; i += nthr) occ4[i] = 0u;
+    if (tid == 0) *ctr = LoaderCounters{0, 0, 0, 0};
+}
+
+// The counters go to the host through mapped pinned memory, written by the GPU itself: a D2H
+// memcpy would queue on the copy engine behind the previous frame's 33 MB readback and stall the
+// stream (pipelined frames, par_submit_frame).
+__global__ void k_publish_counters(const LoaderCounters* ctr, LoaderCounters* host_a, LoaderCounters* host_b) {
+    const LoaderCounters c = *ctr;
+    if (host_a) *host_a = c;
+    if (host_b) *host_b = c;
+}
+
+// Host-side launcher (called from par_api.cu).  host_a / host_b: page-locked host copies of the
+// counters (either may be NULL).
 cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,
                                 const ViewDims& d, int4* boxes, int* cnt, int* ids,
                                 unsigned* occ4, int* survivors, LoaderCounters* ctr,
+                                LoaderCounters* host_a, LoaderCounters* host_b,
                                 cudaStream_t s, int* launches) {
-    cudaError_t err;
-    if ((err = cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)d.V, s))) return err;
-    if ((err = cudaMemsetAsync(ids, 0xff, sizeof(int) * (size_t)d.V * kSlots, s))) return err;
-    if ((err = cudaMemsetAsync(occ4, 0, sizeof(unsigned) * (((size_t)d.V + 7) / 8), s))) return err;
-    if ((err = cudaMemsetAsync(ctr, 0, sizeof(LoaderCounters), s))) return err;
+    static_assert(kSlots % 4 == 0, "k_clear_grid writes the slots as int4");
+    const int clear_blocks = (int)std::min<size_t>(((size_t)d.V * (kSlots / 4) + 255) / 256, 148 * 8);
+    k_clear_grid<<<clear_blocks > 0 ? clear_blocks : 1, 256, 0, s>>>(cnt, ids, occ4, ctr, d.V);
+    *launches += 1;
     if (n > 0) {
         int blocks = (n + 255) / 256;
         k_load_cull_insert<<<blocks, 256, 0, s>>>(raw, sprite_ids, n, n_sprites, d, boxes, cnt, ids,
@@ -90,6 +116,10 @@ cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, i
         // entity survives) and let surplus threads exit on the device-side count.
         k_occupancy<<<blocks, 256, 0, s>>>(survivors, boxes, d, cnt, occ4, ctr);
         *launches += 2;
+    }
+    if (host_a || host_b) {
+        k_publish_counters<<<1, 1, 0, s>>>(ctr, host_a, host_b);
+        *launches += 1;
     }
     return cudaGetLastError();
 }

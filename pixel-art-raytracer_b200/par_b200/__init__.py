@@ -39,7 +39,7 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_rebuild_grid", "par_render", "par_render_device", "par_device_frame",
            "par_render_device_striped", "par_staging_bytes", "par_unstripe_device",
            "par_peer_export", "par_peer_import", "par_peer_set", "par_render_device_peers", "par_read_frame",
-           "par_read_stripes", "par_register_host", "par_unregister_host",
+           "par_read_stripes", "par_register_host", "par_unregister_host", "par_submit_frame", "par_wait_frame",
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
            "par_debug_phase_timing",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
@@ -58,7 +58,7 @@ class Stats(C.Structure):
                 ("ms_total", C.c_float), ("kernel_launches", C.c_int32),
                 ("n_entities", C.c_int32), ("n_survivors", C.c_int32), ("n_inserts", C.c_int32),
                 ("rays", C.c_uint64), ("slab_tests", C.c_uint64), ("ms_walks", C.c_float),
-                ("reserved", C.c_int32 * 3)]
+                ("ms_readback", C.c_float), ("reserved", C.c_int32 * 2)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -120,6 +120,8 @@ def lib():
         L.par_render_device_peers.argtypes = [vp, vp, i32]
         L.par_read_frame.argtypes = [vp, vp]
         L.par_read_stripes.argtypes = [vp, vp]
+        L.par_submit_frame.argtypes = [vp, vp, vp, i32, vp, i32, vp]
+        L.par_wait_frame.argtypes = [vp, vp]
         L.par_register_host.argtypes = [vp, C.c_size_t]
         L.par_unregister_host.argtypes = [vp]
         L.par_device_frame.argtypes = [vp]
@@ -334,6 +336,22 @@ class Renderer:
         out = np.zeros((self.H, self.W), COLOR) if out is None else out
         _check(lib().par_read_frame(self._h, _p(out)))
         return out
+
+    def submit_frame(self, aabbs, lights, out, sprite_ids=None):
+        """par_submit_frame: upload + build + render + readback of one frame, without waiting (<= 2 in
+        flight).  `aabbs` and `out` should come from pinned_empty() and stay untouched until wait_frame()."""
+        assert aabbs.dtype == AABB and aabbs.flags.c_contiguous
+        assert out.shape == (self.H, self.W) and out.dtype == COLOR and out.flags.c_contiguous
+        lights = np.ascontiguousarray(lights, LIGHT)
+        if sprite_ids is not None:
+            assert sprite_ids.dtype == np.int32 and sprite_ids.flags.c_contiguous
+        _check(lib().par_submit_frame(self._h, _p(aabbs), _p(sprite_ids), len(aabbs), _p(lights), len(lights), _p(out)))
+
+    def wait_frame(self):
+        """par_wait_frame: block until the oldest submitted frame is complete in its `out`; returns its stats."""
+        st = Stats()
+        _check(lib().par_wait_frame(self._h, C.byref(st)))
+        return st.as_dict()
 
     def read_stripes(self, host_frame):
         """D2H of the rows this context owns into their place in a full (H, W) host frame (async)."""

@@ -402,6 +402,87 @@ def test_register_host_memory(par):
         par.lib().par_unregister_host(buf.ctypes.data)
 
 
+@pytest.mark.parametrize("stripes", [1, 2])
+def test_pipelined_frames_moving_scene(par, oracle, stripes):
+    """par_submit_frame / par_wait_frame: 24 frames of key script D (player and light move every
+    frame), two in flight, each with its own pinned AABB array and host frame.  Every frame equals
+    the synchronous par_render of the same scene; with 2 striped contexts feeding the same host
+    frames the union is the full frame."""
+    W, H, L = 640, 480, 480
+    boxes, lights = par.scene_default(), par.light_default()
+    scenes, light_seq = [], []
+    for f in range(24):
+        for k in oracle.script_keys("D", f):
+            par.apply_key(k, boxes, lights)
+        scenes.append(boxes.copy())
+        light_seq.append(lights.copy())
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        want = []
+        for f in range(24):
+            r.set_scene(scenes[f])
+            want.append(r.render(light_seq[f])[0].copy())
+    assert any(not np.array_equal(_u32(want[0]), _u32(w)) for w in want[1:])  # the scene does move
+    kw = [dict(stripe_count=stripes, stripe_index=i) if stripes > 1 else {} for i in range(stripes)]
+    rens = [par.Renderer(W, H, L, **k) for k in kw]
+    try:
+        h_boxes = [par.pinned_empty(len(boxes), par.AABB) for _ in range(2)]
+        h_out = [par.pinned_empty((H, W), par.COLOR) for _ in range(2)]
+        for r in rens:
+            r.set_atlas()
+        for f in range(25):
+            if f < 24:
+                h_boxes[f & 1][:] = scenes[f]
+                for r in rens:
+                    r.submit_frame(h_boxes[f & 1], light_seq[f], h_out[f & 1])
+            if f >= 1:
+                for r in rens:
+                    st = r.wait_frame()
+                    assert st["ms_total"] > 0 and st["rays"] == W * H * 2 // stripes
+                assert np.array_equal(_u32(h_out[(f - 1) & 1]), _u32(want[f - 1])), f"frame {f - 1}"
+        # synchronous calls work again once nothing is in flight
+        rens[0].set_scene(scenes[3])
+        part, _ = rens[0].render(light_seq[3])
+        own = np.zeros(H, bool)
+        for t in range(0, H // 40, stripes):
+            own[t * 40:t * 40 + 40] = True
+        assert np.array_equal(_u32(part[own]), _u32(want[3][own]))
+    finally:
+        for r in rens:
+            r.close()
+
+
+def test_pipelined_frames_call_order_and_errors(par):
+    from par_b200 import AABB
+    W, H, L = 480, 320, 320
+    boxes, lights = par.scene_default(), par.light_default()
+    out = [par.pinned_empty((H, W), par.COLOR) for _ in range(3)]
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        with pytest.raises(par.ParError) as e:
+            r.wait_frame()
+        assert e.value.code == -6  # nothing in flight
+        bad = np.array([(10, 0, 10, 30, 20, 20, (0, 0))], AABB)
+        r.submit_frame(boxes, lights, out[0])
+        r.submit_frame(bad, lights, out[1])
+        with pytest.raises(par.ParError) as e:
+            r.submit_frame(boxes, lights, out[2])
+        assert e.value.code == -6  # two in flight
+        with pytest.raises(par.ParError) as e:
+            r.render(lights)
+        assert e.value.code == -6  # synchronous call while frames are in flight
+        r.wait_frame()  # frame 0 is fine
+        with pytest.raises(par.ParError) as e:
+            r.wait_frame()  # frame 1 had the bad scene
+        assert e.value.code == -5
+        r.set_scene(boxes)
+        want, _ = r.render(lights)
+        assert np.array_equal(_u32(out[0]), _u32(want))
+        r.submit_frame(boxes, lights, out[2])  # still usable
+        r.wait_frame()
+        assert np.array_equal(_u32(out[2]), _u32(want))
+
+
 def test_determinism_and_rebuild_idempotence(par):
     W, H, L = 1920, 1080, 1080
     boxes, lights = par.scene_synthetic(W, H, L, n=10000, n_lights=8)
