@@ -242,29 +242,30 @@ def ours(args):
             exchange = "nccl"
     trace(f"exchange = {exchange}")
 
-    # Host-side frame at N > 1: ONE frame in shared memory, page-locked by every rank; each rank
-    # DMAs the stripes it rendered straight into it over its own PCIe link (par_read_stripes).
-    shared = None
+    # Host-side frames at N > 1: two frames (alternating) in shared memory, page-locked by every rank;
+    # each rank DMAs the stripes it rendered straight into them over its own PCIe link.
+    shared = shared2 = None
     if world > 1:
         name = [f"/dev/shm/par_bench_{os.getpid()}" if rank == 0 else None]
         dist.broadcast_object_list(name, src=0)
         try:
             if rank == 0:
-                shared = par.shared_host_frame(name[0], H, W, create=True)
+                shared2 = par.shared_host_frame(name[0], H, W, create=True, frames=2)
             dist.barrier()
             if rank != 0:
-                shared = par.shared_host_frame(name[0], H, W, create=False)
+                shared2 = par.shared_host_frame(name[0], H, W, create=False, frames=2)
+            shared = shared2[0]
             ok = torch.ones(1, dtype=torch.int32, device=dev)
         except Exception as e:
             trace(f"shared host frame unavailable: {e}")
             ok = torch.zeros(1, dtype=torch.int32, device=dev)
-            if rank == 0 and shared is None:
+            if rank == 0 and shared2 is None:
                 dist.barrier()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         if rank == 0 and os.path.exists(name[0]):
             os.unlink(name[0])                   # the mappings keep it alive
         if int(ok.item()) == 0:
-            shared = None
+            shared = shared2 = None
     trace(f"shared host frame: {shared is not None}")
 
     def render_and_gather():
@@ -300,33 +301,46 @@ def ours(args):
         elif rank == 0:
             t_hframe.copy_(frame, non_blocking=True)  # D2H of the gathered frame
 
+    sig_stream = torch.cuda.Stream(device=dev)
+
     def timed_pipelined(steps, warmup):
-        """e2e at N = 1 through par_submit_frame / par_wait_frame: two frames in flight, every step
-        uploads the scene from pinned memory and reads its frame back into pinned memory; the timed
-        region starts with an empty pipeline and ends when the last frame is complete on the host."""
-        h_out = [h_frame, par.pinned_empty((H, W), par.COLOR)]
-        with torch.cuda.stream(stream):
-            for i in range(warmup + 1):
-                if i < warmup:
-                    ren.submit_frame(h_boxes, lights, h_out[i & 1])
-                if i:
-                    ren.wait_frame()
-            barrier()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(stream)
-            t0 = time.perf_counter()
-            for i in range(steps + 1):
-                if i < steps:
+        """e2e through par_submit_frame / par_wait_frame: two frames in flight, every step uploads the
+        scene from pinned memory and reads its frame back into pinned memory (at N > 1: every rank
+        its own stripes, into the shared host frames; after each completed frame a 4-byte all-reduce
+        on a side stream tells every rank that the whole frame is on the host).  The timed region
+        starts with an empty pipeline and ends when the last frame is complete on the host."""
+        h_out = [h_frame, par.pinned_empty((H, W), par.COLOR)] if world == 1 else [shared2[0], shared2[1]]
+
+        def run(n):
+            for i in range(n + 1):
+                if i < n:
                     flush.fill_(1)               # L2 flush between iterations (inside the timed region here)
                     ren.submit_frame(h_boxes, lights, h_out[i & 1])
                 if i:
                     ren.wait_frame()
+                    if world > 1:
+                        with torch.cuda.stream(sig_stream):
+                            dist.all_reduce(token)
+            sig_stream.synchronize()
+
+        with torch.cuda.stream(stream):
+            run(warmup)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            t0 = time.perf_counter()
+            run(steps)
             b.record(stream)
             barrier()
             t1 = time.perf_counter()
-        if (steps - 1) & 1:                      # the check below looks at h_frame
-            h_frame[:] = h_out[1]
-        return a.elapsed_time(b), t0, t1
+        if (steps - 1) & 1:                      # the frame check looks at h_out[0]
+            h_out[0][:] = h_out[1]
+        ms = a.elapsed_time(b)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, t0, t1
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -386,7 +400,8 @@ def ours(args):
     trace("resident timing done")
     ms_e2e, _, t1 = timed(step_e2e, args.steps, max(1, args.warmup // 2))
     ms_e2e_sync = ms_e2e
-    if world == 1:
+    pipelined = world == 1 or shared2 is not None
+    if pipelined:
         ms_e2e, _, t1 = timed_pipelined(args.steps, max(2, args.warmup // 2))
     trace("e2e timing done")
     clocks = sampler.stop(t_load0 - args.prewarm_ms / 1e3, t1) if sampler else None  # pre-warm + timed regions: under load
@@ -493,11 +508,14 @@ def ours(args):
                 "readback": ("each rank DMAs its own stripes into one shared pinned host frame (N PCIe links)"
                              if shared is not None else "rank 0 / the one context copies the whole frame"),
                 "api": ("par_submit_frame / par_wait_frame, two frames in flight (readback of frame k beside upload "
-                        "and kernels of frame k+1); timed from an empty pipeline to the last frame complete on the "
-                        "host, L2 flush inside the timed region" if world == 1 else
+                        "and kernels of frame k+1, the frame's GPU work as one CUDA graph launch); timed from an "
+                        "empty pipeline to the last frame complete on the host, L2 flush inside the timed region"
+                        + ("" if world == 1 else "; every rank ships its own stripes, a 4-byte all-reduce per frame "
+                                                 "signals completion") if pipelined else
                         "par_set_scene + par_render_device + par_read_stripes per rank, barrier per step"),
-                "sync_call_ms": round(ms_e2e_sync / args.steps, 4) if world == 1 else None,
-                "sync_call": "par_set_scene + par_render (blocking drop-in call) per step" if world == 1 else None},
+                "sync_call_ms": round(ms_e2e_sync / args.steps, 4),
+                "sync_call": ("par_set_scene + par_render (blocking drop-in call) per step" if world == 1 else
+                              "par_set_scene + par_render_device + par_read_stripes per rank, barrier per step")},
         "gpu_launches": ((6 if world == 1 or exchange in ("peer", "root") else 7) * args.steps) * world,
         "kernels_ms": {"scene_loader": round(sum(build_ms) / len(build_ms), 4),
                        "k_primary": round(sum(prim_ms) / len(prim_ms), 4), "k_shade": round(shade, 4)},

@@ -217,14 +217,15 @@ def pinned_empty(shape, dtype) -> np.ndarray:
 _PINNED: dict[int, int] = {}
 
 
-def shared_host_frame(path: str, H: int, W: int, create: bool) -> np.ndarray:
-    """(H, W) COLOR frame in a shared-memory file, page-locked in THIS process (par_register_host):
-    several one-GPU processes DMA their stripes into the same host frame (par_read_stripes)."""
-    n = H * W * COLOR.itemsize
+def shared_host_frame(path: str, H: int, W: int, create: bool, frames: int = 1) -> np.ndarray:
+    """(H, W) COLOR frame — or (frames, H, W) of them — in a shared-memory file, page-locked in THIS
+    process (par_register_host): several one-GPU processes DMA their stripes into the same host
+    frame (par_read_stripes, par_submit_frame)."""
+    n = frames * H * W * COLOR.itemsize
     if create:
         with open(path, "wb") as f:
             f.truncate(n)
-    arr = np.memmap(path, dtype=COLOR, mode="r+", shape=(H, W))
+    arr = np.memmap(path, dtype=COLOR, mode="r+", shape=(H, W) if frames == 1 else (frames, H, W))
     _check(lib().par_register_host(arr.ctypes.data, n))
     return arr
 
