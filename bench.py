@@ -484,6 +484,13 @@ def ours(args):
         roofline["traffic"] = traffic["dram_bytes_read"] + traffic["dram_bytes_write"]
         roofline["traffic_source"] = traffic["source"] + " (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per launch)"
         roofline["ncu_issue_active_pct"] = traffic.get("smsp_issue_active_pct")
+        if traffic.get("warp_instructions"):
+            # what the SMs actually issued: ncu's warp-instruction count of one launch x 32 lanes / live time
+            ex = traffic["warp_instructions"] * 32 / (shade * 1e-3) / 1e12
+            roofline["executed"] = {"warp_instructions_per_launch": traffic["warp_instructions"],
+                                    "achieved": round(ex, 2), "frac": round(ex / peak_ops, 3), "unit": "Tlane-op/s",
+                                    "note": "issue-slot utilisation of k_shade: executed warp instructions (ncu "
+                                            "smsp__inst_executed.sum) x 32 / CUDA-event time / the same peak"}
     hbm_bytes = 16.0 * W * my_rows + 4.0 * W * my_rows
     roofline["hbm"] = {"algorithmic_bytes_per_launch": hbm_bytes, "achieved_gbs": round(hbm_bytes / (shade * 1e-3) / 1e9, 1),
                        "peak_gbs": peaks.get("hbm_gbs"), "note": "G-buffer read + RGBA8 write; not the bound"}

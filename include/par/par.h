@@ -208,6 +208,14 @@ int par_read_stripes(par_ctx* ctx, par_color* host_frame);
 int par_submit_frame(par_ctx* ctx, const par_aabb* aabbs, const int32_t* sprite_ids, int n,
                      const par_light* lights, int n_lights, par_color* out_rgba);
 int par_wait_frame(par_ctx* ctx, par_stats* stats);
+/* The reference keeps a pointer to the G-buffer record under the mouse cursor (mouse_pixel,
+ * alternative.cpp:380-382) for its debug overlay (762-772).  par_set_cursor selects that pixel
+ * (it must be one this context renders; x < 0 switches the probe off); from then on every
+ * frame also delivers its 28-byte record — no G-buffer readback needed for the overlay.
+ * par_cursor_pixel returns the record of the frame most recently completed by par_render /
+ * par_wait_frame (after par_render_device it waits for the stream first). */
+int par_set_cursor(par_ctx* ctx, int x, int y);
+int par_cursor_pixel(par_ctx* ctx, par_pixel* out);
 /* Page-lock / unlock host memory the caller already owns (e.g. a shared-memory frame), so that
  * copies into it are asynchronous DMA. */
 int par_register_host(void* p, size_t bytes);
@@ -265,9 +273,13 @@ void par_scene_synthetic(int width, int height, int length, uint64_t seed, int n
 /* Key semantics of alternative.cpp:641-681 on entity 0 / light 0.  key: 'L','R' arrows,
  * 'U','D' arrows, 'P'/'p' page up/down, and the literal light keys a k j u h o. */
 void par_apply_key(int key, par_aabb* player, par_light* light);
-/* Debug overlay of alternative.cpp:139-175, 762-772 drawn into a host frame. */
+/* Debug overlay of alternative.cpp:139-175, 762-772 drawn into a host frame: a red line from the
+ * surface point under the cursor to light 0.  par_draw_overlay reads the record from a whole
+ * G-buffer, par_draw_overlay_at takes the single record (par_cursor_pixel). */
 void par_draw_overlay(int width, int height, const par_pixel* gbuf, const par_light* light,
                       int cursor_x, int cursor_y, par_color* frame);
+void par_draw_overlay_at(int width, int height, const par_pixel* under_cursor, const par_light* light,
+                         int cursor_x, par_color* frame);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -135,7 +135,13 @@ class FrameRenderer {
         cfg.device = device;
         check(par_create(&ctx_, &cfg));
     }
-    ~FrameRenderer() { par_destroy(ctx_); }
+    ~FrameRenderer() {
+        par_destroy(ctx_);
+        for (Staging& st : staging_) {
+            par_free_host(st.aabbs);
+            par_free_host(st.sprite_ids);
+        }
+    }
     FrameRenderer(const FrameRenderer&) = delete;
     FrameRenderer& operator=(const FrameRenderer&) = delete;
 
@@ -145,13 +151,7 @@ class FrameRenderer {
     template <int N>
     void render_frame(Entities<N>& entities, const std::vector<Light>& lights, Color* p_texture,
                       Pixel* p_pixel_buffer = nullptr, par_stats* stats = nullptr) {
-        static const par_color palette[4] = {{100, 100, 100, 0}, {140, 140, 140, 0},
-                                             {200, 200, 200, 0}, {240, 240, 240, 0}};  // sprites.hpp:60-65
-        if (entities.atlas_dirty) {
-            check(par_set_atlas(ctx_, reinterpret_cast<const par_sprite*>(entities.sprite_pool.data()),
-                                static_cast<int>(entities.sprite_pool.size()), palette, 4));
-            entities.atlas_dirty = false;
-        }
+        update_atlas(entities);
         check(par_set_scene(ctx_, reinterpret_cast<const par_aabb*>(entities.aabbs.data()),
                             entities.sprite_ids.data(), entities.size()));
         check(par_render(ctx_, reinterpret_cast<const par_light*>(lights.data()),
@@ -159,13 +159,72 @@ class FrameRenderer {
                          reinterpret_cast<par_pixel*>(p_pixel_buffer), stats));
     }
 
+    // Throughput form of render_frame: up to two frames in flight.  submit_frame snapshots the
+    // entities into page-locked staging (so the caller may move them right away) and returns;
+    // wait_frame blocks until the OLDEST submitted frame is complete in the p_texture it was given
+    // (allocate it with alloc_frame(): page-locked memory keeps the readback asynchronous).
+    template <int N>
+    void submit_frame(Entities<N>& entities, const std::vector<Light>& lights, Color* p_texture) {
+        update_atlas(entities);
+        Staging& st = staging_[next_ & 1];
+        const size_t n = static_cast<size_t>(entities.size());
+        if (n > st.capacity) {
+            par_free_host(st.aabbs);
+            par_free_host(st.sprite_ids);
+            st.capacity = n + n / 8 + 64;
+            st.aabbs = static_cast<par_aabb*>(par_alloc_host(st.capacity * sizeof(par_aabb)));
+            st.sprite_ids = static_cast<int32_t*>(par_alloc_host(st.capacity * sizeof(int32_t)));
+            if (!st.aabbs || !st.sprite_ids) throw Error(PAR_ERR_OUT_OF_MEMORY, par_last_error());
+        }
+        std::memcpy(st.aabbs, entities.aabbs.data(), n * sizeof(par_aabb));
+        std::memcpy(st.sprite_ids, entities.sprite_ids.data(), n * sizeof(int32_t));
+        check(par_submit_frame(ctx_, st.aabbs, st.sprite_ids, static_cast<int>(n),
+                               reinterpret_cast<const par_light*>(lights.data()), static_cast<int>(lights.size()),
+                               reinterpret_cast<par_color*>(p_texture)));
+        next_++;
+    }
+    void wait_frame(par_stats* stats = nullptr) { check(par_wait_frame(ctx_, stats)); }
+
+    // The record under the mouse cursor (mouse_pixel, alternative.cpp:380-382) of the frame
+    // most recently completed, for the debug overlay.
+    void set_cursor(int x, int y) { check(par_set_cursor(ctx_, x, y)); }
+    Pixel cursor_pixel() {
+        Pixel p;
+        check(par_cursor_pixel(ctx_, reinterpret_cast<par_pixel*>(&p)));
+        return p;
+    }
+
+    static Color* alloc_frame(int view_width, int view_height) {
+        void* p = par_alloc_host(static_cast<size_t>(view_width) * view_height * sizeof(Color));
+        if (!p) throw Error(PAR_ERR_OUT_OF_MEMORY, par_last_error());
+        return static_cast<Color*>(p);
+    }
+    static void free_frame(Color* p) { par_free_host(p); }
+
     par_ctx* handle() { return ctx_; }
 
   private:
+    struct Staging {
+        par_aabb* aabbs = nullptr;
+        int32_t* sprite_ids = nullptr;
+        size_t capacity = 0;
+    };
+    template <int N>
+    void update_atlas(Entities<N>& entities) {
+        static const par_color palette[4] = {{100, 100, 100, 0}, {140, 140, 140, 0},
+                                             {200, 200, 200, 0}, {240, 240, 240, 0}};  // sprites.hpp:60-65
+        if (entities.atlas_dirty) {
+            check(par_set_atlas(ctx_, reinterpret_cast<const par_sprite*>(entities.sprite_pool.data()),
+                                static_cast<int>(entities.sprite_pool.size()), palette, 4));
+            entities.atlas_dirty = false;
+        }
+    }
     static void check(int rc) {
         if (rc != PAR_OK) throw Error(rc, par_last_error());
     }
     par_ctx* ctx_ = nullptr;
+    Staging staging_[2];
+    unsigned next_ = 0;
 };
 
 }  // namespace par

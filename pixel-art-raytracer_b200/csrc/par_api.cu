@@ -14,14 +14,10 @@ namespace par {
 
 // Expand the compact G-buffer into the reference's Pixel records (sprites.hpp:53-58) and a
 // texel-index plane, for the parity checkpoints of par_get_gbuffer / par_render(out_gbuf).
-__global__ void __launch_bounds__(256)
-k_expand_gbuf(const int4* __restrict__ gbuf, const float* __restrict__ atlas_normal,
-              const unsigned char* __restrict__ atlas_color, const uchar4* __restrict__ palette,
-              size_t first, size_t count, int* __restrict__ out_pixel7, int* __restrict__ out_texel) {
-    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= count) return;
-    size_t px = first + t;
-    int4 g = gbuf[px];
+// Compact G-buffer record -> the reference's 28-byte Pixel (normal, colour, y, z, entity) + texel index.
+__device__ __forceinline__ int expand_pixel(int4 g, const float* __restrict__ atlas_normal,
+                                            const unsigned char* __restrict__ atlas_color,
+                                            const uchar4* __restrict__ palette, int o[7]) {
     float nx = 0.f, ny = 0.f, nz = 0.f;
     uchar4 c = make_uchar4(127, 127, 127, 0);  // alternative.cpp:281
     int texel = -1;
@@ -34,17 +30,41 @@ k_expand_gbuf(const int4* __restrict__ gbuf, const float* __restrict__ atlas_nor
         nz = nrm[2];
         c = palette[atlas_color[spr * kTexels + texel]];
     }
-    if (out_pixel7) {
-        int* o = out_pixel7 + px * 7;
-        o[0] = __float_as_int(nx);
-        o[1] = __float_as_int(ny);
-        o[2] = __float_as_int(nz);
-        o[3] = (int)((unsigned)c.x | (unsigned)c.y << 8 | (unsigned)c.z << 16 | (unsigned)c.w << 24);
-        o[4] = g.y;
-        o[5] = g.z;
-        o[6] = g.x;
-    }
+    o[0] = __float_as_int(nx);
+    o[1] = __float_as_int(ny);
+    o[2] = __float_as_int(nz);
+    o[3] = (int)((unsigned)c.x | (unsigned)c.y << 8 | (unsigned)c.z << 16 | (unsigned)c.w << 24);
+    o[4] = g.y;
+    o[5] = g.z;
+    o[6] = g.x;
+    return texel;
+}
+
+__global__ void __launch_bounds__(256)
+k_expand_gbuf(const int4* __restrict__ gbuf, const float* __restrict__ atlas_normal,
+              const unsigned char* __restrict__ atlas_color, const uchar4* __restrict__ palette,
+              size_t first, size_t count, int* __restrict__ out_pixel7, int* __restrict__ out_texel) {
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= count) return;
+    size_t px = first + t;
+    int o[7];
+    const int texel = expand_pixel(gbuf[px], atlas_normal, atlas_color, palette, o);
+    if (out_pixel7)
+        for (int k = 0; k < 7; k++) out_pixel7[px * 7 + k] = o[k];
     if (out_texel) out_texel[px] = texel;
+}
+
+// The reference's cursor probe (mouse_pixel, alternative.cpp:380-382): the record of ONE pixel,
+// stored straight into mapped pinned host memory (no copy-engine traffic, see k_publish_counters).
+__global__ void k_probe_pixel(const int4* __restrict__ gbuf, const float* __restrict__ atlas_normal,
+                              const unsigned char* __restrict__ atlas_color, const uchar4* __restrict__ palette,
+                              size_t px, int* host_a, int* host_b) {
+    int o[7];
+    expand_pixel(gbuf[px], atlas_normal, atlas_color, palette, o);
+    for (int k = 0; k < 7; k++) {
+        if (host_a) host_a[k] = o[k];
+        if (host_b) host_b[k] = o[k];
+    }
 }
 
 // Stripe-major staging frame ([n][T][40][W] uchar4) -> raster frame, 16 bytes per thread.
@@ -131,6 +151,11 @@ struct par_ctx {
     uchar4* d_frame_alt = nullptr;  // slot 1's frame, allocated on first use (slot 0 uses d_frame)
     cudaEvent_t ev_slot_begin[2] = {}, ev_slot_kernels[2] = {}, ev_slot_done[2] = {};
     int slots_in_flight = 0, slot_oldest = 0, slot_next = 0, slot_lights[2] = {};
+    // cursor probe: [0] frames of the synchronous calls, [1 + slot] pipelined frames (pinned, 7 ints each)
+    int cursor_x = -1, cursor_y = -1;
+    int (*h_probe)[7] = nullptr;
+    int (*probe_slot)[7] = nullptr;    // where the frame being submitted also stores its probe
+    int (*probe_latest)[7] = nullptr;  // record of the frame par_cursor_pixel reports
     bool capturing = false;            // a pipelined frame is being captured into frame_exec
     cudaGraphExec_t frame_exec = nullptr;  // upload + build + kernels of one pipelined frame as ONE graph launch
     float last_kernel_ms = 0.f;  // primary + shade of the previous par_render (pipelining heuristic)
@@ -269,6 +294,8 @@ int par_create(par_ctx** out, const par_config* cfg) {
         PAR_CUDA(cudaMalloc(&c->d_ctr, sizeof(LoaderCounters)));
         PAR_CUDA(cudaMallocHost(&c->h_ctr, 3 * sizeof(LoaderCounters)));  // [0] latest build, [1 + slot] pipelined frames
         memset(c->h_ctr, 0, 3 * sizeof(LoaderCounters));
+        PAR_CUDA(cudaMallocHost(&c->h_probe, 3 * sizeof(int[7])));
+        memset(c->h_probe, 0, 3 * sizeof(int[7]));
         for (int k = 0; k < 2; k++) {
             PAR_CUDA(cudaEventCreate(&c->ev_slot_begin[k]));
             PAR_CUDA(cudaEventCreate(&c->ev_slot_kernels[k]));
@@ -308,6 +335,7 @@ void par_destroy(par_ctx* c) {
     cudaFree(c->d_occ4);
     cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->h_probe) cudaFreeHost(c->h_probe);
     cudaFree(c->d_atlas_depth);
     cudaFree(c->d_atlas_normal);
     cudaFree(c->d_atlas_color);
@@ -628,13 +656,22 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
             }
         }
     }
+    int probe_launch = 0;
+    if (c->cursor_x >= 0) {  // the record under the cursor goes to the host with every frame
+        k_probe_pixel<<<1, 1, 0, c->stream>>>(c->d_gbuf, c->d_atlas_normal, c->d_atlas_color, c->d_palette,
+                                              (size_t)c->cursor_y * d.W + c->cursor_x, c->h_probe[0],
+                                              pipelined ? *c->probe_slot : nullptr);
+        PAR_CUDA(cudaGetLastError());
+        probe_launch = 1;
+        if (!pipelined) c->probe_latest = &c->h_probe[0];
+    }
     PAR_CUDA(record_timing(c, c->ev_f2));
     if (host_out && n_chunks > 1) {  // make the context's stream cover the copies too
         PAR_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
         PAR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_copy, 0));
     }
     c->n_chunks = n_chunks;
-    c->launches_frame = (use_walks ? 3 : 2) * n_chunks;
+    c->launches_frame = (use_walks ? 3 : 2) * n_chunks + probe_launch;
     c->last_n_lights = n_lights;
     c->frame_valid = true;
     c->frame_timed = !c->capturing;
@@ -776,6 +813,7 @@ int par_submit_frame(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_id
         PAR_CUDA(cudaMemsetAsync(c->d_frame_alt, 0, sizeof(uchar4) * px, c->stream));
     }
     uchar4* d_out = slot ? c->d_frame_alt : c->d_frame;
+    c->probe_slot = &c->h_probe[1 + slot];
     PAR_CUDA(cudaEventRecord(c->ev_slot_begin[slot], c->stream));
     // Upload, grid build and both kernels go to the GPU as ONE graph launch: while the previous
     // frame's readback saturates PCIe, every separate launch costs ~25 us of command fetch latency
@@ -847,6 +885,7 @@ int par_wait_frame(par_ctx* c, par_stats* stats) {
     c->slot_oldest = slot ^ 1;
     c->slots_in_flight--;
     PAR_CUDA(cudaEventSynchronize(c->ev_slot_done[slot]));
+    c->probe_latest = &c->h_probe[1 + slot];
     const LoaderCounters& lc = c->h_ctr[1 + slot];
     if (stats) {
         memset(stats, 0, sizeof *stats);
@@ -859,6 +898,36 @@ int par_wait_frame(par_ctx* c, par_stats* stats) {
         stats->rays = owned_row_count(c) * c->d.W * (1 + (uint64_t)c->slot_lights[slot]);
     }
     return lc.bad_scene ? bad_scene_error() : PAR_OK;
+}
+
+int par_set_cursor(par_ctx* c, int x, int y) {
+    if (!c) return fail(PAR_ERR_INVALID_ARG, "par_set_cursor: null context%s%s");
+    if (x < 0 || y < 0) {
+        c->cursor_x = c->cursor_y = -1;
+        c->probe_latest = nullptr;
+        return PAR_OK;
+    }
+    const ViewDims& d = c->d;
+    const int n = d.stripe_n > 1 ? d.stripe_n : 1;
+    if (x >= d.W || y < d.row0 || y >= d.row1 || (y / kBin) % n != (n > 1 ? d.stripe_i : 0))
+        return fail(PAR_ERR_INVALID_ARG, "par_set_cursor: the pixel is not one this context renders%s%s");
+    c->cursor_x = x;
+    c->cursor_y = y;
+    c->probe_latest = nullptr;
+    return PAR_OK;
+}
+
+int par_cursor_pixel(par_ctx* c, par_pixel* out) {
+    if (!c || !out) return fail(PAR_ERR_INVALID_ARG, "par_cursor_pixel: null argument%s%s");
+    if (!c->probe_latest)
+        return fail(PAR_ERR_STATE, "par_cursor_pixel: no frame rendered since par_set_cursor%s%s");
+    if (c->probe_latest == &c->h_probe[0]) {  // frame of a synchronous / device call: it may still be running
+        DeviceGuard guard(c->cfg.device);
+        PAR_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    static_assert(sizeof(par_pixel) == sizeof(int[7]), "Pixel is 7 words");
+    memcpy(out, *c->probe_latest, sizeof(par_pixel));
+    return PAR_OK;
 }
 
 int par_register_host(void* p, size_t bytes) {

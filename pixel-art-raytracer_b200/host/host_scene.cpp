@@ -162,7 +162,12 @@ void par_apply_key(int key, par_aabb* player, par_light* light) {  // alternativ
 // only the view height.
 void par_draw_overlay(int width, int height, const par_pixel* gbuf, const par_light* light,
                       int cursor_x, int cursor_y, par_color* frame) {
-    const par_pixel& under = gbuf[static_cast<size_t>(cursor_y) * width + cursor_x];
+    par_draw_overlay_at(width, height, &gbuf[static_cast<size_t>(cursor_y) * width + cursor_x], light, cursor_x, frame);
+}
+
+void par_draw_overlay_at(int width, int height, const par_pixel* under_cursor, const par_light* light,
+                         int cursor_x, par_color* frame) {
+    const par_pixel& under = *under_cursor;
     int x = cursor_x, y = height - (under.y + under.z);
     const int x_end = light->x, y_end = height - (light->y + light->z);
     const int span_x = std::abs(x_end - x), span_y = -std::abs(y_end - y);

@@ -5,7 +5,12 @@
 // debug overlay (762-772) and prints one "%03d %016llx" FNV-1a-64 line per frame — the same
 // format the SDL stub of oracle/ uses for the real reference, so the two can be diffed.
 //
-//   par_headless [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm out.ppm]
+// Default: frames are pipelined (FrameRenderer::submit_frame / wait_frame, two in flight): while
+// the GPU renders frame k the host draws the overlay of frame k-1 and hashes it; the overlay's
+// record under the cursor comes from the cursor probe, not from a G-buffer readback.
+// --sync: the blocking render_frame with the whole G-buffer, the reference's call shape.
+//
+//   par_headless [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm out.ppm] [--sync] [--no-hash]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -43,6 +48,7 @@ int main(int argc, char** argv) {
     int W = 480, H = 320, L = 320, frames = 1, device = 0;
     char script = 0;
     const char* ppm = nullptr;
+    bool sync = false, hash = true;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--view") && i + 3 < argc) {
             W = atoi(argv[++i]);
@@ -56,8 +62,12 @@ int main(int argc, char** argv) {
             device = atoi(argv[++i]);
         } else if (!strcmp(argv[i], "--ppm") && i + 1 < argc) {
             ppm = argv[++i];
+        } else if (!strcmp(argv[i], "--sync")) {
+            sync = true;
+        } else if (!strcmp(argv[i], "--no-hash")) {  // frame rate of the loop without the checker's FNV pass
+            hash = false;
         } else {
-            fprintf(stderr, "usage: %s [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm f]\n", argv[0]);
+            fprintf(stderr, "usage: %s [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm f] [--sync] [--no-hash]\n", argv[0]);
             return 2;
         }
     }
@@ -68,35 +78,66 @@ int main(int argc, char** argv) {
         par_light_default(reinterpret_cast<par_light*>(lights.data()));  // alternative.cpp:624-626
 
         par::FrameRenderer renderer(W, H, L, device);
-        std::vector<par::Color> texture(static_cast<size_t>(W) * H);
-        std::vector<par::Pixel> gbuf(static_cast<size_t>(W) * H);
-        double gpu_ms = 0, wall_ms = 0;
-        for (int f = 0; f < frames; f++) {
+        const size_t px = static_cast<size_t>(W) * H;
+        par::Color* texture[2] = {par::FrameRenderer::alloc_frame(W, H), par::FrameRenderer::alloc_frame(W, H)};
+        par::Color* last = texture[0];
+        auto apply_script = [&](int f) {
             if (script == 'C' || script == 'D') {
                 par_aabb* player = reinterpret_cast<par_aabb*>(&entities.aabbs[0]);
                 par_light* light = reinterpret_cast<par_light*>(&lights[0]);
                 if (int k = script_c_key(f)) par_apply_key(k, player, light);
                 if (script == 'D' && f >= 1) par_apply_key('o', player, light);
             }
-            par_stats st{};
-            auto t0 = std::chrono::steady_clock::now();
-            renderer.render_frame(entities, lights, texture.data(), gbuf.data(), &st);
-            wall_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
-            gpu_ms += st.ms_grid_build + st.ms_total;
-            par_draw_overlay(W, H, reinterpret_cast<const par_pixel*>(gbuf.data()),
-                             reinterpret_cast<const par_light*>(&lights[0]), 0, 0,
-                             reinterpret_cast<par_color*>(texture.data()));
-            printf("%03d %016llx\n", f, fnv1a64(reinterpret_cast<const unsigned char*>(texture.data()), texture.size() * 4));
+        };
+        auto finish = [&](int f, par::Color* tex, const par::Pixel& under, const par::Light& light) {
+            par_draw_overlay_at(W, H, reinterpret_cast<const par_pixel*>(&under),
+                                reinterpret_cast<const par_light*>(&light), 0, reinterpret_cast<par_color*>(tex));
+            if (hash) printf("%03d %016llx\n", f, fnv1a64(reinterpret_cast<const unsigned char*>(tex), px * 4));
+            last = tex;
+        };
+        double gpu_ms = 0;
+        const auto t0 = std::chrono::steady_clock::now();
+        if (sync) {
+            std::vector<par::Pixel> gbuf(px);
+            for (int f = 0; f < frames; f++) {
+                apply_script(f);
+                par_stats st{};
+                renderer.render_frame(entities, lights, texture[0], gbuf.data(), &st);
+                gpu_ms += st.ms_grid_build + st.ms_total;
+                finish(f, texture[0], gbuf[0], lights[0]);  // cursor at (0, 0), like the headless reference
+            }
+        } else {
+            renderer.set_cursor(0, 0);
+            par::Light light_of[2];
+            for (int f = 0; f <= frames; f++) {
+                if (f < frames) {
+                    apply_script(f);
+                    light_of[f & 1] = lights[0];
+                    renderer.submit_frame(entities, lights, texture[f & 1]);
+                }
+                if (f >= 1) {
+                    par_stats st{};
+                    renderer.wait_frame(&st);
+                    gpu_ms += st.ms_total;
+                    finish(f - 1, texture[(f - 1) & 1], renderer.cursor_pixel(), light_of[(f - 1) & 1]);
+                }
+            }
         }
-        fprintf(stderr, "%d frame(s) %dx%dx%d: %.3f ms/frame on the GPU (loader + kernels), %.3f ms/frame wall incl. "
-                        "upload, G-buffer and frame readback\n", frames, W, H, L, gpu_ms / frames, wall_ms / frames);
+        const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "%d frame(s) %dx%dx%d, %s: %.3f ms/frame wall (scene update, upload, render, readback, overlay%s) "
+                        "= %.1f frames/s; %.3f ms/frame %s\n", frames, W, H, L,
+                sync ? "blocking render_frame + G-buffer" : "pipelined submit_frame/wait_frame + cursor probe",
+                wall_ms / frames, hash ? ", FNV hash" : "", 1e3 * frames / wall_ms, gpu_ms / frames,
+                sync ? "on the GPU (loader + kernels)" : "submit -> frame on the host (latency)");
         if (ppm) {
             FILE* fp = fopen(ppm, "wb");
             if (!fp) return 1;
             fprintf(fp, "P6\n%d %d\n255\n", W, H);
-            for (const par::Color& c : texture) fwrite(&c, 1, 3, fp);
+            for (size_t i = 0; i < px; i++) fwrite(&last[i], 1, 3, fp);
             fclose(fp);
         }
+        par::FrameRenderer::free_frame(texture[0]);
+        par::FrameRenderer::free_frame(texture[1]);
     } catch (const par::Error& e) {
         fprintf(stderr, "par error %d: %s\n", e.code, e.what());
         return 1;

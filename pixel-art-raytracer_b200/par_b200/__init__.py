@@ -43,7 +43,8 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
            "par_debug_phase_timing",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
-           "par_light_default", "par_scene_synthetic", "par_apply_key", "par_draw_overlay"]
+           "par_light_default", "par_scene_synthetic", "par_apply_key", "par_draw_overlay",
+           "par_draw_overlay_at", "par_set_cursor", "par_cursor_pixel"]
 
 
 class Config(C.Structure):
@@ -144,6 +145,10 @@ def lib():
         L.par_apply_key.restype = None
         L.par_draw_overlay.argtypes = [i32, i32, vp, vp, i32, i32, vp]
         L.par_draw_overlay.restype = None
+        L.par_draw_overlay_at.argtypes = [i32, i32, vp, vp, i32, vp]
+        L.par_draw_overlay_at.restype = None
+        L.par_set_cursor.argtypes = [vp, i32, i32]
+        L.par_cursor_pixel.argtypes = [vp, vp]
         _lib = L
     return _lib
 
@@ -199,6 +204,12 @@ def apply_key(key: str, boxes: np.ndarray, lights: np.ndarray) -> None:
 
 def draw_overlay(W, H, gbuf, lights, frame, cx=0, cy=0) -> None:
     lib().par_draw_overlay(W, H, _p(gbuf), _p(lights), cx, cy, _p(frame))
+
+
+def draw_overlay_at(W, H, under_cursor, lights, frame, cx=0) -> None:
+    """Overlay from the single record under the cursor (Renderer.cursor_pixel())."""
+    under = np.ascontiguousarray(under_cursor, PIXEL).reshape(1)
+    lib().par_draw_overlay_at(W, H, _p(under), _p(lights), cx, _p(frame))
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:
@@ -337,6 +348,16 @@ class Renderer:
         out = np.zeros((self.H, self.W), COLOR) if out is None else out
         _check(lib().par_read_frame(self._h, _p(out)))
         return out
+
+    def set_cursor(self, x: int, y: int):
+        """Select the pixel whose G-buffer record every frame also delivers (mouse_pixel); x < 0: off."""
+        _check(lib().par_set_cursor(self._h, x, y))
+
+    def cursor_pixel(self) -> np.ndarray:
+        """PIXEL record under the cursor of the frame most recently completed."""
+        out = np.zeros(1, PIXEL)
+        _check(lib().par_cursor_pixel(self._h, _p(out)))
+        return out[0]
 
     def submit_frame(self, aabbs, lights, out, sprite_ids=None):
         """par_submit_frame: upload + build + render + readback of one frame, without waiting (<= 2 in

@@ -138,13 +138,15 @@ def test_multi_single_device_is_plain(par):
     assert np.array_equal(one.view(np.uint32), many.view(np.uint32))
 
 
-def test_headless_driver_prints_reference_hashes(par, golden):
+@pytest.mark.parametrize("mode", [[], ["--sync"]])
+def test_headless_driver_prints_reference_hashes(par, golden, mode):
     """C++ host (Entities::insert + FrameRenderer + overlay) vs the UNMODIFIED reference's
-    per-frame FNV-1a-64 hashes under key script C."""
+    per-frame FNV-1a-64 hashes under key script C — pipelined frames with the cursor probe
+    (default) and the blocking render_frame with the whole G-buffer (--sync)."""
     exe = os.path.join(PKG, "build", "par_headless")
     if not os.path.exists(exe):
         pytest.skip("par_headless not built")
-    out = subprocess.run([exe, "--frames", "40", "--script", "C"], check=True, capture_output=True, text=True).stdout
+    out = subprocess.run([exe, "--frames", "40", "--script", "C"] + mode, check=True, capture_output=True, text=True).stdout
     got = [ln.split()[1] for ln in out.splitlines()]
     assert got == golden["tier0_480x320x320_scriptC_240"]["fnv1a64"][:40]
 
@@ -157,6 +159,7 @@ def test_headless_driver_full_c4_sequence(par, golden):
     exe = os.path.join(PKG, "build", "par_headless")
     if not os.path.exists(exe):
         pytest.skip("par_headless not built")
-    out = subprocess.run([exe, "--view", "1920", "1080", "1080", "--frames", "240", "--script", "D"],
-                         check=True, capture_output=True).stdout
-    assert hashlib.sha256(out).hexdigest() == golden["tier1_1920x1080x1080_scriptD_240"]["hash_file_sha256"]
+    res = subprocess.run([exe, "--view", "1920", "1080", "1080", "--frames", "240", "--script", "D"],
+                         check=True, capture_output=True)
+    print(res.stderr.decode())  # frames/s of the sequence (shown with pytest -s / on failure)
+    assert hashlib.sha256(res.stdout).hexdigest() == golden["tier1_1920x1080x1080_scriptD_240"]["hash_file_sha256"]

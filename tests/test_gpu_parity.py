@@ -452,6 +452,59 @@ def test_pipelined_frames_moving_scene(par, oracle, stripes):
             r.close()
 
 
+def test_cursor_probe_and_overlay(par, oracle):
+    """par_set_cursor / par_cursor_pixel: the record under the cursor arrives with every frame
+    (blocking and pipelined) and equals the G-buffer's; the overlay drawn from it equals the one
+    drawn from the whole G-buffer."""
+    W, H, L = 640, 480, 480
+    boxes, lights = par.scene_default(), par.light_default()
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        with pytest.raises(par.ParError) as e:
+            r.set_cursor(W, 0)
+        assert e.value.code == -1
+        r.set_cursor(300, 200)
+        with pytest.raises(par.ParError) as e:
+            r.cursor_pixel()
+        assert e.value.code == -6  # nothing rendered yet
+        outs = [par.pinned_empty((H, W), par.COLOR) for _ in range(2)]
+        hb = [par.pinned_empty(len(boxes), par.AABB) for _ in range(2)]
+        for f in range(6):
+            for k in oracle.script_keys("D", f):
+                par.apply_key(k, boxes, lights)
+            for cx, cy in ((300, 200), (0, 0), (639, 479)):
+                r.set_cursor(cx, cy)
+                r.set_scene(boxes)
+                rgba, gbuf, _ = r.render(lights, want_gbuf=True)
+                under = r.cursor_pixel()
+                assert under.tobytes() == gbuf[cy, cx].tobytes()
+                a, b = rgba.copy(), rgba.copy()
+                par.draw_overlay(W, H, gbuf, lights, a, cx, cy)
+                par.draw_overlay_at(W, H, under, lights, b, cx)
+                assert np.array_equal(_u32(a), _u32(b))
+                r.render_device(lights)  # asynchronous call: cursor_pixel waits for it
+                assert r.cursor_pixel().tobytes() == gbuf[cy, cx].tobytes()
+            # pipelined, two in flight with different cursors: each wait_frame brings ITS frame's record
+            r.set_scene(boxes)
+            _, gbuf, _ = r.render(lights, want_gbuf=True)
+            hb[0][:] = boxes
+            r.set_cursor(300, 200)
+            r.submit_frame(hb[0], lights, outs[0])
+            r.set_cursor(5, 470)
+            r.submit_frame(hb[0], lights, outs[1])
+            r.wait_frame()
+            assert r.cursor_pixel().tobytes() == gbuf[200, 300].tobytes(), f"pipelined frame {f}a"
+            r.wait_frame()
+            assert r.cursor_pixel().tobytes() == gbuf[470, 5].tobytes(), f"pipelined frame {f}b"
+        r.set_cursor(-1, -1)
+        with pytest.raises(par.ParError):
+            r.cursor_pixel()
+    with par.Renderer(W, H, L, stripe_count=2, stripe_index=1) as r:
+        r.set_cursor(10, 45)  # tile row 1: owned
+        with pytest.raises(par.ParError):
+            r.set_cursor(10, 5)  # tile row 0: rank 0's
+
+
 def test_pipelined_frames_call_order_and_errors(par):
     from par_b200 import AABB
     W, H, L = 480, 320, 320
