@@ -57,3 +57,10 @@ def test_overlay(par, oracle, golden):
     par.draw_overlay(480, 320, r["gbuf"], lights2, f1, 100, 200)
     O.draw_overlay(480, 320, 320, r["gbuf"], lights2, f2, 100, 200)
     assert np.array_equal(f1.view(np.uint32), f2.view(np.uint32))
+    # the single-record form (cursor probe, mouse_pixel of alternative.cpp:380-382) draws the same line
+    f3 = r["rgba"].copy()
+    par.draw_overlay_at(480, 320, r["gbuf"][200, 100], lights2, f3, 100)
+    assert np.array_equal(f1.view(np.uint32), f3.view(np.uint32))
+    f4 = r["rgba"].copy()
+    par.draw_overlay_at(480, 320, r["gbuf"][0, 0], lights, f4, 0)
+    assert sha256(f4) == golden["tier0_480x320x320_frame0"]["frame0_sha256"]
