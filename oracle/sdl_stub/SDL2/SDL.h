@@ -22,6 +22,12 @@
  *                    sed-instrumented tier-1 build calls just before draw_line
  *                    (alternative.cpp:762): the shaded frame without the debug overlay and
  *                    the raw Pixel[] G-buffer, for the frames in PAR_REF_DUMP_FRAMES
+ *   PAR_REF_SCENE    file read by par_stub_load_scene(), a second hook of the tier-1 build
+ *                    (called once, just before the frame loop, alternative.cpp:628): replaces
+ *                    the built-in scene and light by the file's — int32 n_boxes, int32
+ *                    n_lights, n_boxes x 8 int16 (position xyz, extent xyz, 2 pad),
+ *                    n_lights x 4 int16 (x y z radius) — through the reference's own
+ *                    Entities::insert, so the REAL reference renders arbitrary scenes
  */
 #pragma once
 #include <chrono>
@@ -29,6 +35,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 struct SDL_Window {};
 struct SDL_Renderer {};
@@ -148,6 +155,48 @@ inline void par_stub_dump_pre(void const* frame, size_t frame_bytes, void const*
         fwrite(gbuf, 1, gbuf_bytes, s.dump_gbuf);
         fflush(s.dump_gbuf);
     }
+}
+
+// Hook for the instrumented tier-1 build only: load scene + lights from PAR_REF_SCENE.
+// Generic over the reference's types (Entities<N>*, std::vector<Light>&); entities go through
+// the reference's own insert() (alternative.cpp:104-109), so sprites etc. are whatever it does.
+template <class EntitiesPtr, class LightVector>
+inline void par_stub_load_scene(EntitiesPtr p_entities, LightVector& lights) {
+    char const* path = getenv("PAR_REF_SCENE");
+    if (!path) return;
+    FILE* f = fopen(path, "rb");
+    int32_t hdr[2] = {0, 0};
+    if (!f || fread(hdr, 4, 2, f) != 2) {
+        fprintf(stderr, "par_stub_load_scene: cannot read %s\n", path);
+        exit(3);
+    }
+    p_entities->aabbs.clear();
+    p_entities->sprites.clear();
+    p_entities->last_entity_index = 0;
+    for (int i = 0; i < hdr[0]; i++) {
+        int16_t v[8];
+        if (fread(v, 2, 8, f) != 8) exit(3);
+        typename std::remove_pointer<EntitiesPtr>::type::Entity e{};
+        e.aabb.position.x = v[0];
+        e.aabb.position.y = v[1];
+        e.aabb.position.z = v[2];
+        e.aabb.extent.x = v[3];
+        e.aabb.extent.y = v[4];
+        e.aabb.extent.z = v[5];
+        p_entities->insert(e);
+    }
+    lights.clear();
+    for (int i = 0; i < hdr[1]; i++) {
+        int16_t v[4];
+        if (fread(v, 2, 4, f) != 4) exit(3);
+        typename LightVector::value_type l{};
+        l.x = v[0];
+        l.y = v[1];
+        l.z = v[2];
+        l.radius = v[3];
+        lights.push_back(l);
+    }
+    fclose(f);
 }
 
 inline int SDL_InitSubSystem(unsigned) { return 0; }

@@ -46,6 +46,26 @@ def golden():
         return json.load(f)
 
 
+@pytest.fixture(scope="session")
+def golden_scenes():
+    """Hashes of what the REAL reference renders for the scene files stored beside them
+    (tests/golden/make_reference_scene_goldens.py)."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "reference_scenes.json")) as f:
+        return json.load(f)
+
+
+def decode_scene(entry, aabb_dtype, light_dtype):
+    """(boxes, lights) of one reference_scenes.json entry as structured arrays."""
+    import base64
+    import numpy as np
+    blob = base64.b64decode(entry["scene_b64"])
+    n, nl = np.frombuffer(blob, np.int32, 2)
+    boxes = np.frombuffer(blob, aabb_dtype, n, 8).copy()
+    lights = np.frombuffer(blob, light_dtype, nl, 8 + 16 * n).copy()
+    return boxes, lights
+
+
 def sha256(arr):
     import hashlib
     import numpy as np

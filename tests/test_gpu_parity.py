@@ -119,6 +119,57 @@ def test_default_scene_large_views_vs_reference_hashes(par, golden, size, key):
     assert sha256(frame) == g["frame0_sha256"]
 
 
+@pytest.mark.parametrize("k", range(16))
+def test_random_scenes_vs_real_reference_hashes(par, oracle, golden_scenes, k):
+    """Scenes the REAL reference rendered through its scene hook (random / ragged / lattice-snapped
+    boxes, the light free or on a box face, views with length != height, scripted frames): the
+    G-buffer bytes, the shaded frame and the final frames from the C ABI hash to the reference's."""
+    from conftest import decode_scene, sha256
+    if k >= len(golden_scenes["scenes"]):
+        pytest.skip("fewer scenes in the golden file")
+    e = golden_scenes["scenes"][k]
+    W, H, L = e["view"]
+    boxes, lights = decode_scene(e, par.AABB, par.LIGHT)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        for f in range(e["frames"]):
+            if e["script"]:
+                for key in oracle.script_keys(e["script"], f):
+                    par.apply_key(key, boxes, lights)
+            r.set_scene(boxes)
+            rgba, gbuf, _ = r.render(lights, want_gbuf=True)
+            if f == 0:
+                assert sha256(gbuf) == e["gbuf0_sha256"]
+                assert sha256(rgba) == e["frame0_pre_overlay_sha256"]
+            par.draw_overlay(W, H, gbuf, lights, rgba)
+            assert "%016x" % oracle.fnv1a64(rgba) == e["fnv1a64"][f], f"frame {f}"
+
+
+@pytest.mark.parametrize("view", ["480x320x320", "480x320x640", "640x480x200", "200x40x40", "40x1000x120"])
+def test_default_scene_other_views_vs_real_reference_hashes(par, oracle, golden_scenes, view):
+    """The built-in scene through views with length != height (light moved inside the grid),
+    3 frames of key script D, against the real reference's hashes."""
+    from conftest import sha256
+    e = golden_scenes["default_scene"].get(view)
+    if e is None:
+        pytest.skip("no golden for this view")
+    W, H, L = e["view"]
+    boxes, lights = par.scene_default(), par.light_default()
+    lights[0]["x"], lights[0]["y"], lights[0]["z"], lights[0]["radius"] = e["light"]
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        for f in range(e["frames"]):
+            for key in oracle.script_keys(e["script"], f):
+                par.apply_key(key, boxes, lights)
+            r.set_scene(boxes)
+            rgba, gbuf, _ = r.render(lights, want_gbuf=True)
+            if f == 0:
+                assert sha256(gbuf) == e["gbuf0_sha256"]
+                assert sha256(rgba) == e["frame0_pre_overlay_sha256"]
+            par.draw_overlay(W, H, gbuf, lights, rgba)
+            assert "%016x" % oracle.fnv1a64(rgba) == e["fnv1a64"][f], f"frame {f}"
+
+
 def test_script_d_frames_vs_reference_hashes(par, oracle, golden):
     """Config 4: per-frame scene upload + render under key script D (player and light move),
     FNV-1a-64 of every sampled frame (overlay applied) against the real reference's."""
