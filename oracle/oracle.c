@@ -365,6 +365,19 @@ static inline int slab_hit(const orc_aabb* b, const orc_ray* r) {
     return tmax >= tmin;
 }
 
+/* The reference's occlusion predicate for ONE box and ONE pixel: ray set-up of
+ * alternative.cpp:712-722 (L1-normalised direction, quirk Q12; reciprocal) + AABB::intersect.
+ * Exported for property tests of exact-output culls (tests/test_shaft_cull_property.py). */
+int orc_slab_hit_point(const orc_aabb* box, int ox, int oy, int oz, const orc_light* lt) {
+    float tx = (float)(lt->x - ox), ty = (float)(lt->y - oy), tz = (float)(lt->z - oz);
+    float len = fabsf(tx) + fabsf(ty) + fabsf(tz);
+    tx = tx / len;
+    ty = ty / len;
+    tz = tz / len;
+    orc_ray ray = {1.f / tx, 1.f / ty, 1.f / tz, (int16_t)ox, (int16_t)oy, (int16_t)oz};
+    return slab_hit(box, &ray);
+}
+
 typedef struct {
     uint64_t probes, entries, slabs;
 } walk_ctr;
