@@ -31,7 +31,7 @@ REF = os.path.join(ROOT, "oracle", "_ref")
 OUT = os.path.join(ROOT, "tests", "golden", "reference_scenes.json")
 
 
-def make_scene(rng, W, H, L, n, n_lights, ragged, lattice, lights_on_boxes):
+def make_scene(rng, W, H, L, n, n_lights, ragged, lattice, lights_on_boxes, frames=1):
     b = np.zeros((n, 8), np.int16)
     b[:, 0] = rng.integers(-30, W + 30, n)
     b[:, 1] = rng.integers(-30, max(H // 2, 40), n)
@@ -46,20 +46,20 @@ def make_scene(rng, W, H, L, n, n_lights, ragged, lattice, lights_on_boxes):
         b[:, 0:3] = (b[:, 0:3] // 20) * 20
     li = np.zeros((n_lights, 4), np.int16)
     for k in range(n_lights):
-        li[k] = light_inside(rng, W, H, L)
+        li[k] = light_inside(rng, W, H, L, frames)
         if lights_on_boxes and k % 2 == 0:  # exactly on a box's top face
             for _ in range(50):
                 e = int(rng.integers(0, n))
                 x2, y2, z2 = int(b[e, 0]) + int(rng.integers(0, 21)), int(b[e, 1]) + int(b[e, 4]), int(b[e, 2]) + int(rng.integers(0, 21))
-                if 5 <= x2 < W - 30 and 5 <= z2 < L - 5 and 5 <= H - y2 - z2 <= H - 5:
+                if 5 <= x2 < W - 10 - 5 * frames and 5 <= z2 < L - 5 and 5 <= H - y2 - z2 <= H - 5:
                     li[k] = (x2, y2, z2, 10)
                     break
     return b, li
 
 
-def light_inside(rng, W, H, L):
-    """A light whose bin (x/40, (H-y-z)/40, z/40) is inside the grid, with room for a few 'o' keys (x += 5)."""
-    x = int(rng.integers(5, max(W - 30, 6)))
+def light_inside(rng, W, H, L, frames=4):
+    """A light whose bin (x/40, (H-y-z)/40, z/40) is inside the grid, with room for one 'o' key (x += 5) per frame."""
+    x = int(rng.integers(5, max(W - 10 - 5 * frames, 6)))
     z = int(rng.integers(5, L - 5))
     row = int(rng.integers(5, H - 4))  # H - y - z
     return (x, H - row - z, z, 10)
@@ -110,6 +110,9 @@ CASES = [  # view, n boxes, ragged, lattice, light on a box face, frames, script
     ((200, 40, 40), 40, False, False, False, 1, None),
     ((40, 1000, 120), 300, True, False, True, 1, None),
     ((40, 1000, 120), 200, False, True, False, 2, "D"),
+    # long scripted runs: entity 0 walks through a ragged scene (bins change under it), the light moves too
+    ((480, 320, 640), 1200, True, False, False, 120, "C"),
+    ((640, 480, 200), 900, True, True, True, 20, "D"),
 ]
 
 
@@ -137,7 +140,7 @@ def main():
         print("scene", k, view, n, flush=True)
         nl = 1
         rng = np.random.default_rng(1000 + k)
-        boxes, lights = make_scene(rng, *view, n, nl, ragged, lattice, on_boxes)
+        boxes, lights = make_scene(rng, *view, n, nl, ragged, lattice, on_boxes, frames)
         blob = scene_bytes(boxes, lights)
         try:
             res = run_reference(view, blob, frames=frames, script=script)

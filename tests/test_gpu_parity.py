@@ -119,7 +119,7 @@ def test_default_scene_large_views_vs_reference_hashes(par, golden, size, key):
     assert sha256(frame) == g["frame0_sha256"]
 
 
-@pytest.mark.parametrize("k", range(16))
+@pytest.mark.parametrize("k", range(18))
 def test_random_scenes_vs_real_reference_hashes(par, oracle, golden_scenes, k):
     """Scenes the REAL reference rendered through its scene hook (random / ragged / lattice-snapped
     boxes, the light free or on a box face, views with length != height, scripted frames): the

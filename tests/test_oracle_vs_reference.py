@@ -143,7 +143,7 @@ def _check_against_reference_entry(O, entry, boxes, lights):
         assert "%016x" % O.fnv1a64(post) == entry["fnv1a64"][f], f"frame {f}"
 
 
-@pytest.mark.parametrize("k", range(16))
+@pytest.mark.parametrize("k", range(18))
 def test_random_scenes_vs_real_reference(oracle, golden_scenes, k):
     """Random / ragged / lattice-snapped scenes, the light free or on a box face, at views with
     length != height too: the oracle's G-buffer, shaded frame and scripted final frames equal the
