@@ -237,18 +237,37 @@ k_shade(const __grid_constant__ ShadeParams p) {
     constexpr int kNoZ = -0x7fffffff - 1;
     auto group_of = [](int z) { return z == kNoZ ? kNoGroup : z / kBin; };
     int zv[kPixPerThread];
+    // (z, texel | sprite << 10) of the thread's pixels, staged through the (still idle) box list
+    // with cp.async: all ten copies of a thread are in flight at once.  As plain loads next to
+    // the per-pixel branches below, the compiler keeps at most three in flight (registers) and
+    // every CTA pays several DRAM round trips in a row before it can start.  Each thread reads
+    // back only what it copied itself, so no barrier is needed — only cp.async.wait_all.
+    int2* const stage = reinterpret_cast<int2*>(s.list);
+    static_assert(sizeof(int2) * kTilePixels <= sizeof(float4) * 2 * kListCap, "tile staging fits the box list");
 #pragma unroll
     for (int m = 0; m < kPixPerThread; m++) {
         const int pidx = m * kThreads + tid;  // pixel (row pidx / 40, column pidx % 40) of the tile
         const int j = ty * kBin + pidx / kBin;
+        if (j >= ra && j < rb) {
+            const int2* src = reinterpret_cast<const int2*>(&p.gbuf[(size_t)j * d.W + bx * kBin + pidx % kBin]) + 1;
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(&stage[pidx]);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+        }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+#pragma unroll
+    for (int m = 0; m < kPixPerThread; m++) {
+        const int pidx = m * kThreads + tid;
+        const int j = ty * kBin + pidx / kBin;
         zv[m] = kNoZ;
         if (j >= ra && j < rb) {
-            const int4 g = __ldcs(&p.gbuf[(size_t)j * d.W + bx * kBin + pidx % kBin]);  // streamed: keep L1 for the grid
-            if (g.w >= 0 && n_lights > 0) {
-                zv[m] = g.z;
+            const int2 zw = stage[pidx];
+            const int gz = zw.x, gw = zw.y;
+            if (gw >= 0 && n_lights > 0) {
+                zv[m] = gz;
             } else {
                 uchar4 c = make_uchar4(127, 127, 127, 0);  // miss colour, alternative.cpp:281
-                if (g.w >= 0) c = p.palette[p.atlas_color[(g.w >> 10) * kTexels + (g.w & 1023)]];
+                if (gw >= 0) c = p.palette[p.atlas_color[(gw >> 10) * kTexels + (gw & 1023)]];
                 s.out[pidx] = quantise(c, std_min(1.f, 0.f + p.ambient));
             }
         }
