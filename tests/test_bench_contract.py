@@ -45,3 +45,18 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     assert res.returncode != 0
     assert "no CUDA device" in (res.stderr + res.stdout)
     assert not any(ln.startswith("{") for ln in res.stdout.splitlines())
+
+
+def test_cpu_baseline_object_of_the_product_arm():
+    """The cpu_baseline leg bench.py attaches to its own line (real reference, 1 thread, plus the
+    oracle port on all cores), run here on C1."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_tier1_480x320x320")):
+        pytest.skip("oracle/_ref not built")
+    import argparse
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_module", BENCH)
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    cb = bench.cpu_baseline(argparse.Namespace(workload="c1", cpu_budget=5.0), 480, 320, 320)
+    assert cb["kind"] == "reference" and cb["cores"] == 1 and cb["unit"] == "Mrays/s" and cb["value"] > 0
+    assert "sample" in cb and cb["port_all_cores"]["kind"] == "port" and cb["port_all_cores"]["value"] > 0
