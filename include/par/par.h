@@ -35,6 +35,9 @@ extern "C" {
 #define PAR_SPRITE_W 20       /* sprite width hard-coded at alternative.cpp:330 */
 #define PAR_SPRITE_H 40
 #define PAR_SPRITE_TEXELS 800 /* sprites.hpp:68-70 */
+#define PAR_MAX_SPRITE_DIM 1024   /* par_set_atlas_sized: width and height of a sprite            */
+#define PAR_MAX_SPRITE_DEPTH 4095 /* ... and |depth| of a texel (world z of a hit stays 16-bit)   */
+#define PAR_MAX_UPDATE 8      /* entities par_update_entities patches in place (more: re-bin all) */
 #define PAR_MAX_LIGHTS 64
 #define PAR_MAX_VIEW 12800    /* W, H, L upper bound (one grid-walk step per thread) */
 
@@ -44,7 +47,7 @@ typedef enum par_status {
     PAR_ERR_NO_DEVICE = -2,     /* no CUDA device / wrong architecture               */
     PAR_ERR_CUDA = -3,          /* a CUDA runtime call failed, see par_last_error()  */
     PAR_ERR_OUT_OF_MEMORY = -4, /* host or device allocation failed                  */
-    PAR_ERR_BAD_SCENE = -5,     /* an AABB would index outside the 20x40 sprite      */
+    PAR_ERR_BAD_SCENE = -5,     /* an inserted AABB would index outside its sprite   */
     PAR_ERR_STATE = -6,         /* call order: atlas and scene must be set first     */
     PAR_ERR_NCCL = -7           /* multi-GPU gather failed                           */
 } par_status;
@@ -90,15 +93,17 @@ typedef struct par_config {
     int32_t stripe_count; /* > 1: of the band, render only the 40-row tile rows t with          */
     int32_t stripe_index; /* t % stripe_count == stripe_index (interleaved stripes balance the   */
                           /* per-row cost over GPUs far better than contiguous bands); 0/1 = all */
-    int32_t reserved[3];
+    int32_t tile_order;   /* longest-tile-first CTA order from the previous frame's per-tile cost: */
+                          /* 0 = automatic (on for >= 2 lights), 1 = always, -1 = never            */
+    int32_t reserved[2];
 } par_config;
 
 /* Filled by par_render / par_get_stats; GPU times are CUDA-event milliseconds on the
  * context's stream for the most recent build / frame. */
 typedef struct par_stats {
     float ms_grid_build;   /* scene loader kernels (cull + bin + select)        */
-    float ms_primary;      /* ray-gen + intersection kernel                     */
-    float ms_shade;        /* shading + shadow + RGBA8 pack kernel              */
+    float ms_render;       /* the render kernel: primary rays + shading + shadow rays + RGBA8 pack */
+    float ms_reserved;     /* (0)                                               */
     float ms_total;        /* first kernel start to last kernel end of the frame */
     int32_t kernel_launches; /* kernels launched by the most recent build + frame */
     int32_t n_entities;
@@ -106,7 +111,7 @@ typedef struct par_stats {
     int32_t n_inserts;     /* (entity, bin) insertions (alternative.cpp:243-267)       */
     uint64_t rays;         /* reference-equivalent rays: rows*W*(1+n_lights)           */
     uint64_t slab_tests;   /* reserved (0)                                              */
-    float ms_walks;        /* shadow-walk kernel (one warp per tile x z-group x light)  */
+    float ms_reserved2;    /* (0)                                                       */
     float ms_readback;     /* par_wait_frame only: kernels done -> frame complete on the host
                             * (queueing behind the previous frame's copy + the D2H itself);
                             * ms_total is submit -> complete, the per-kernel times stay 0 */
@@ -137,6 +142,16 @@ void par_free_host(void* p);
 int par_set_atlas(par_ctx* ctx, const par_sprite* sprites, int n_sprites,
                   const par_color* palette, int n_palette);
 
+/* Same with per-sprite dimensions (lifts quirk Q7: the reference hard-codes a 20-texel row at
+ * alternative.cpp:330 and 800 texels per sprite at sprites.hpp:68-70).  Sprite s is widths[s] x
+ * heights[s] texels (1..PAR_MAX_SPRITE_DIM each), row-major; the three tables hold the sprites
+ * back to back (color: palette index, depth: |d| <= PAR_MAX_SPRITE_DEPTH, normal: 3 floats per
+ * texel).  A texel index is row * widths[s] + column; an entity of sprite s must have
+ * extent.x <= widths[s] and extent.y + extent.z <= heights[s] (else PAR_ERR_BAD_SCENE). */
+int par_set_atlas_sized(par_ctx* ctx, int n_sprites, const int32_t* widths, const int32_t* heights,
+                        const int32_t* color, const int32_t* depth, const float* normal,
+                        const par_color* palette, int n_palette);
+
 /* Per-frame scene: replaces Entities::aabbs (alternative.cpp:94) and runs the device scene
  * loader = memset + count_entities_in_bins (alternative.cpp:690-693).  sprite_ids may be
  * NULL (every entity uses atlas entry 0, which is what Entities::insert produces,
@@ -146,6 +161,16 @@ int par_set_scene(par_ctx* ctx, const par_aabb* aabbs, const int32_t* sprite_ids
 
 /* Re-run the device scene loader on the scene already resident in HBM (no upload). */
 int par_rebuild_grid(par_ctx* ctx);
+
+/* Incremental scene update: entities [first, first + count) of the RESIDENT scene get new boxes
+ * (and, with sprite_ids != NULL, new sprites).  The reference's input handling moves one entity
+ * per key (alternative.cpp:641-660) yet re-bins all of them every frame (689-693); here up to
+ * PAR_MAX_UPDATE entities are patched in place — their 16-byte records travel as kernel
+ * arguments, and only the bins their old and new boxes span are rebuilt — so a moving player
+ * costs 16 bytes of upload instead of the whole scene.  Larger updates upload the range and
+ * re-bin everything on the device.  The resulting grid is identical to a full par_set_scene. */
+int par_update_entities(par_ctx* ctx, int first, int count, const par_aabb* aabbs,
+                        const int32_t* sprite_ids);
 
 /* -- frame ---------------------------------------------------------------------------- */
 /* Render one frame and read it back.  out_rgba: host, W*H par_color, caller-owned; rows of
@@ -208,6 +233,32 @@ int par_read_stripes(par_ctx* ctx, par_color* host_frame);
 int par_submit_frame(par_ctx* ctx, const par_aabb* aabbs, const int32_t* sprite_ids, int n,
                      const par_light* lights, int n_lights, par_color* out_rgba);
 int par_wait_frame(par_ctx* ctx, par_stats* stats);
+/* par_submit_frame for a scene that is already resident: applies par_update_entities(first, count,
+ * aabbs, sprite_ids) (count may be 0) and renders — no scene upload at all.  aabbs may be any host
+ * memory and may be reused as soon as the call returns. */
+int par_submit_update(par_ctx* ctx, int first, int count, const par_aabb* aabbs, const int32_t* sprite_ids,
+                      const par_light* lights, int n_lights, par_color* out_rgba);
+/* Row pitch, in bytes, of every HOST frame this context writes (par_render, par_submit_*,
+ * par_read_frame, par_read_stripes): the blit contract of alternative.cpp:774-788, where the
+ * destination is a locked texture with its own pitch.  0 (default) = packed rows of W * 4 bytes. */
+int par_set_output_pitch(par_ctx* ctx, size_t pitch_bytes);
+/* D2H of the whole raster frame into rows `pitch_bytes` apart (one strided DMA, asynchronous for
+ * pinned memory) — SDL_LockTexture + the row loop + SDL_UnlockTexture of alternative.cpp:774-783. */
+int par_read_frame_pitched(par_ctx* ctx, void* dst, size_t pitch_bytes);
+
+/* Render a frame from the RESIDENT scene: device scene loader + render kernel, asynchronously on
+ * the context's stream, into the context's own frame (par_device_frame).  The launch sequence is
+ * captured once into CUDA graphs and replayed while the lights stay the same.  With an exchange
+ * set up (par_exchange_setup) the call also carries the multi-GPU frame exchange: the render
+ * kernel's stores go to the consumers' frames as well, arrival is signalled through flags in the
+ * consumers' frame footers, consumers wait for all producers on their stream, and a producer does
+ * not overwrite a consumer's frame before that consumer has started its next call — no NCCL
+ * collective, no host round trip. */
+int par_render_resident(par_ctx* ctx, const par_light* lights, int n_lights);
+/* Multi-GPU exchange of par_render_resident for striped contexts: every other rank must have been
+ * imported (par_peer_import / par_peer_set).  root >= 0: gather-to-root (only that rank's frame
+ * is completed); root = -1: all-gather (every rank's frame is completed). */
+int par_exchange_setup(par_ctx* ctx, int root);
 /* The reference keeps a pointer to the G-buffer record under the mouse cursor (mouse_pixel,
  * alternative.cpp:380-382) for its debug overlay (762-772).  par_set_cursor selects that pixel
  * (it must be one this context renders; x < 0 switches the probe off); from then on every
@@ -229,6 +280,14 @@ void* par_device_frame(par_ctx* ctx);
  *   count  int32[volume]  (p_aabb_count_in_bin), ids int32[volume*8] (entity-index map in
  *          slot order; slots >= count[bin] are -1).  Any pointer may be NULL. */
 int par_get_gbuffer(par_ctx* ctx, par_pixel* gbuf, int32_t* texel);
+/* fp32 intermediates of the most recent frame, recomputed by the render kernel itself with the
+ * export switched on (SURVEY.md 8d "Tolerance"): t_lam = W*H x 4 floats, the L1-normalised
+ * direction towards light `light` (alternative.cpp:711-715) and its Lambert term (745-747);
+ * factor = W*H floats, acc + ambient (the operand of the final min, alternative.cpp:757-758).
+ * Only hit pixels are written (the kernel never evaluates t for a miss pixel, quirk Q19); the
+ * rest stays 0.  lights must be the ones the frame was rendered with.  Either may be NULL. */
+int par_debug_intermediates(par_ctx* ctx, const par_light* lights, int n_lights, int light,
+                            float* t_lam, float* factor);
 int par_get_grid(par_ctx* ctx, int32_t* count, int32_t* ids);
 int par_get_stats(par_ctx* ctx, par_stats* stats);
 int par_grid_volume(const par_ctx* ctx);

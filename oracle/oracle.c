@@ -67,6 +67,20 @@ typedef struct {
     int32_t W, H, L; /* view_width / view_height / view_length */
 } orc_view;
 
+/* Sprite atlas with per-entry dimensions (lifts quirk Q7: the reference hard-codes width 20 at
+ * alternative.cpp:330 and 800 texels at sprites.hpp:68-70).  Sprite s is w[s] x h[s] texels,
+ * row-major, at off[s] in the three concatenated tables; texel index = row * w[s] + column,
+ * which reduces to the reference's row * 20 + column for the 20x40 sprite. */
+typedef struct {
+    int32_t n;
+    const int32_t* w;
+    const int32_t* h;
+    const int32_t* off;
+    const int32_t* color;
+    const int32_t* depth;
+    const float* normal; /* 3 floats per texel */
+} orc_atlas;
+
 /* §8(d) counters, in the order of SURVEY.md's weight table. */
 typedef struct {
     uint64_t pixels, primary_bins, primary_slot_tests, primary_passed, primary_accepts;
@@ -274,10 +288,10 @@ void orc_grid_build(const orc_view* v, const orc_aabb* boxes, int n, int32_t* co
 /* alternative.cpp:271-383 for rows [row0,row1).  gbuf: orc_pixel[W*H] (only the band is
  * written); texel: optional int32[W*H] (sprite texel index of the winning hit, -1 = miss);
  * sprite_ids: optional per-entity atlas index (NULL = all 0). */
-void orc_trace_primary(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
-                       const int32_t* bin_ent, const orc_sprite* atlas, const int32_t* sprite_ids,
-                       const orc_color* palette, orc_pixel* gbuf, int32_t* texel, int row0,
-                       int row1, orc_counters* ctr) {
+static void trace_primary_atlas(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
+                                const int32_t* bin_ent, const orc_atlas* atlas, const int32_t* sprite_ids,
+                                const orc_color* palette, orc_pixel* gbuf, int32_t* texel, int row0,
+                                int row1, orc_counters* ctr) {
     const int W = v->W, H = v->H, HL = hl(v);
     uint64_t c_bins = 0, c_tests = 0, c_pass = 0, c_acc = 0, c_hit = 0;
 #pragma omp parallel for schedule(dynamic, 8) reduction(+ : c_bins, c_tests, c_pass, c_acc, c_hit)
@@ -304,18 +318,19 @@ void orc_trace_primary(const orc_view* v, const int32_t* count, const orc_aabb* 
                         continue; /* quirk Q6 */
                     c_pass++;
                     int ent = bin_ent[(size_t)f * ORC_SLOTS + k];
-                    const orc_sprite* sp = &atlas[sprite_ids ? sprite_ids[ent] : 0];
+                    const int sid = sprite_ids ? sprite_ids[ent] : 0;
+                    const int base = atlas->off[sid];
                     int row = top - world_j;
-                    int idx = row * ORC_SPR_W + (i - b->px); /* quirk Q7 */
-                    int d = sp->depth[idx];
+                    int idx = row * atlas->w[sid] + (i - b->px); /* quirk Q7, width per sprite */
+                    int d = atlas->depth[base + idx];
                     int key = b->py - b->pz + imin(0, b->ey - row) - d; /* quirk Q8 */
                     if (best >= key) continue;
                     c_acc++;
                     best = key;
-                    px.nx = sp->normal[idx][0];
-                    px.ny = sp->normal[idx][1];
-                    px.nz = sp->normal[idx][2];
-                    px.color = palette[sp->color[idx]];
+                    px.nx = atlas->normal[3 * (size_t)(base + idx) + 0];
+                    px.ny = atlas->normal[3 * (size_t)(base + idx) + 1];
+                    px.nz = atlas->normal[3 * (size_t)(base + idx) + 2];
+                    px.color = palette[atlas->color[base + idx]];
                     px.y = b->py + b->ey + b->ez - row - d; /* quirk Q11 */
                     px.z = b->pz + d;
                     px.entity = ent;
@@ -338,6 +353,56 @@ void orc_trace_primary(const orc_view* v, const int32_t* count, const orc_aabb* 
         ctr->primary_accepts += c_acc;
         ctr->pixels_hit += c_hit;
     }
+}
+
+/* The reference's fixed 20x40 sprites (sprites.hpp:67-71) as a ragged atlas.  Returns 0 / -1. */
+typedef struct {
+    orc_atlas a;
+    int32_t *w, *h, *off, *color, *depth;
+    float* normal;
+} atlas_store;
+
+static void atlas_free(atlas_store* st) {
+    free(st->w);
+    free(st->h);
+    free(st->off);
+    free(st->color);
+    free(st->depth);
+    free(st->normal);
+    memset(st, 0, sizeof *st);
+}
+
+static int atlas_from_sprites(const orc_sprite* sprites, int n, atlas_store* st) {
+    memset(st, 0, sizeof *st);
+    size_t nt = (size_t)n * ORC_SPR_TEXELS;
+    st->w = malloc(sizeof(int32_t) * (size_t)n);
+    st->h = malloc(sizeof(int32_t) * (size_t)n);
+    st->off = malloc(sizeof(int32_t) * (size_t)n);
+    st->color = malloc(sizeof(int32_t) * nt);
+    st->depth = malloc(sizeof(int32_t) * nt);
+    st->normal = malloc(sizeof(float) * 3 * nt);
+    if (!st->w || !st->h || !st->off || !st->color || !st->depth || !st->normal) {
+        atlas_free(st);
+        return -1;
+    }
+    for (int s = 0; s < n; s++) {
+        st->w[s] = ORC_SPR_W;
+        st->h[s] = ORC_SPR_TEXELS / ORC_SPR_W;
+        st->off[s] = s * ORC_SPR_TEXELS;
+        memcpy(st->color + (size_t)s * ORC_SPR_TEXELS, sprites[s].color, sizeof sprites[s].color);
+        memcpy(st->depth + (size_t)s * ORC_SPR_TEXELS, sprites[s].depth, sizeof sprites[s].depth);
+        memcpy(st->normal + 3 * (size_t)s * ORC_SPR_TEXELS, sprites[s].normal, sizeof sprites[s].normal);
+    }
+    st->a = (orc_atlas){n, st->w, st->h, st->off, st->color, st->depth, st->normal};
+    return 0;
+}
+
+/* Number of atlas entries the scene refers to (max sprite id + 1). */
+static int atlas_entries_used(const int32_t* sprite_ids, int n) {
+    int m = 0;
+    if (sprite_ids)
+        for (int e = 0; e < n; e++) m = imax(m, sprite_ids[e]);
+    return m + 1;
 }
 
 /* ------------------------------------------------------------------ shadow rays */
@@ -436,9 +501,10 @@ static inline orc_color color_scale(orc_color c, float s) {
 /* alternative.cpp:702-760 for rows [row0,row1), N lights:
  *   acc = sum over visible lights of max(0, n . t_l);  out = color * min(1, acc + 0.25)
  * which is bit-identical to the reference for one light. */
-void orc_shade(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
-               const int32_t* bin_ent, const orc_pixel* gbuf, const orc_light* lights,
-               int n_lights, orc_color* out, int row0, int row1, orc_counters* ctr) {
+static void shade_impl(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
+                       const int32_t* bin_ent, const orc_pixel* gbuf, const orc_light* lights,
+                       int n_lights, orc_color* out, int row0, int row1, orc_counters* ctr,
+                       int dbg_light, float* dbg_t, float* dbg_factor) {
     const int W = v->W, H = v->H;
     const float ambient = 0.25f;
     uint64_t c_shaded = 0, c_lit = 0, c_probe = 0, c_entry = 0, c_slab = 0;
@@ -468,12 +534,21 @@ void orc_shade(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
                 c_probe += wc.probes;
                 c_entry += wc.entries;
                 c_slab += wc.slabs;
+                float dot = px->nx * tx + px->ny * ty + px->nz * tz;
+                float lam = std_maxf(0.f, dot);
+                if (dbg_t && l == dbg_light) { /* fp32 intermediates of SURVEY.md §8(d) "Tolerance" */
+                    float* o = dbg_t + 4 * ((size_t)j * W + i);
+                    o[0] = tx;
+                    o[1] = ty;
+                    o[2] = tz;
+                    o[3] = lam;
+                }
                 if (vis) {
                     c_lit++;
-                    float dot = px->nx * tx + px->ny * ty + px->nz * tz;
-                    acc = acc + std_maxf(0.f, dot);
+                    acc = acc + lam;
                 }
             }
+            if (dbg_factor) dbg_factor[(size_t)j * W + i] = acc + ambient;
             out[(size_t)j * W + i] = color_scale(px->color, std_minf(1.f, acc + ambient));
         }
     }
@@ -484,6 +559,12 @@ void orc_shade(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
         ctr->shadow_slot_entries += c_entry;
         ctr->slab_tests += c_slab;
     }
+}
+
+void orc_shade(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
+               const int32_t* bin_ent, const orc_pixel* gbuf, const orc_light* lights,
+               int n_lights, orc_color* out, int row0, int row1, orc_counters* ctr) {
+    shade_impl(v, count, bin_box, bin_ent, gbuf, lights, n_lights, out, row0, row1, ctr, -1, NULL, NULL);
 }
 
 /* ------------------------------------------------------------------ debug overlay */
@@ -520,12 +601,16 @@ void orc_draw_overlay(const orc_view* v, const orc_pixel* gbuf, const orc_light*
 
 /* ------------------------------------------------------------------ whole frame */
 
-/* The reference frame loop body alternative.cpp:689-760 (no overlay) for rows [row0,row1).
- * Scratch for the grid is allocated per call.  Returns 0, or -1 on allocation failure. */
-int orc_render_frame(const orc_view* v, const orc_aabb* boxes, const int32_t* sprite_ids, int n,
-                     const orc_sprite* atlas, const orc_color* palette, const orc_light* lights,
-                     int n_lights, orc_color* out_rgba, orc_pixel* out_gbuf, int32_t* out_texel,
-                     int row0, int row1, orc_counters* ctr) {
+/* The reference frame loop body alternative.cpp:689-760 (no overlay) for rows [row0,row1), over a
+ * ragged atlas.  Scratch for the grid is allocated per call.  dbg_*: optional fp32 intermediates
+ * of light dbg_light — t.xyz and the Lambert term (4 floats per pixel) — and acc + ambient (1
+ * float per pixel), the operands SURVEY.md §8(d) puts a <= 1 ULP tolerance on.
+ * Returns 0, or -1 on allocation failure. */
+int orc_render_frame_atlas(const orc_view* v, const orc_aabb* boxes, const int32_t* sprite_ids, int n,
+                           const orc_atlas* atlas, const orc_color* palette, const orc_light* lights,
+                           int n_lights, orc_color* out_rgba, orc_pixel* out_gbuf, int32_t* out_texel,
+                           int row0, int row1, orc_counters* ctr, int dbg_light, float* dbg_t,
+                           float* dbg_factor) {
     size_t V = (size_t)orc_grid_volume(v);
     int32_t* count = malloc(sizeof(int32_t) * V);
     orc_aabb* bin_box = malloc(sizeof(orc_aabb) * V * ORC_SLOTS);
@@ -533,14 +618,41 @@ int orc_render_frame(const orc_view* v, const orc_aabb* boxes, const int32_t* sp
     orc_pixel* gbuf = out_gbuf ? out_gbuf : malloc(sizeof(orc_pixel) * (size_t)v->W * v->H);
     if (!count || !bin_box || !bin_ent || !gbuf) return -1;
     orc_grid_build(v, boxes, n, count, bin_box, bin_ent);
-    orc_trace_primary(v, count, bin_box, bin_ent, atlas, sprite_ids, palette, gbuf, out_texel,
-                      row0, row1, ctr);
+    trace_primary_atlas(v, count, bin_box, bin_ent, atlas, sprite_ids, palette, gbuf, out_texel,
+                        row0, row1, ctr);
     if (out_rgba)
-        orc_shade(v, count, bin_box, bin_ent, gbuf, lights, n_lights, out_rgba, row0, row1, ctr);
+        shade_impl(v, count, bin_box, bin_ent, gbuf, lights, n_lights, out_rgba, row0, row1, ctr,
+                   dbg_light, dbg_t, dbg_factor);
     if (!out_gbuf) free(gbuf);
     free(count);
     free(bin_box);
     free(bin_ent);
+    return 0;
+}
+
+/* Same with the reference's fixed 20x40 Sprite records (sprites.hpp:67-71). */
+int orc_render_frame(const orc_view* v, const orc_aabb* boxes, const int32_t* sprite_ids, int n,
+                     const orc_sprite* atlas, const orc_color* palette, const orc_light* lights,
+                     int n_lights, orc_color* out_rgba, orc_pixel* out_gbuf, int32_t* out_texel,
+                     int row0, int row1, orc_counters* ctr) {
+    atlas_store st;
+    if (atlas_from_sprites(atlas, atlas_entries_used(sprite_ids, n), &st)) return -1;
+    int rc = orc_render_frame_atlas(v, boxes, sprite_ids, n, &st.a, palette, lights, n_lights, out_rgba,
+                                    out_gbuf, out_texel, row0, row1, ctr, -1, NULL, NULL);
+    atlas_free(&st);
+    return rc;
+}
+
+/* alternative.cpp:271-383 with the fixed Sprite records (kept for callers that drive the passes
+ * one by one). */
+int orc_trace_primary(const orc_view* v, const int32_t* count, const orc_aabb* bin_box,
+                      const int32_t* bin_ent, const orc_sprite* atlas, int n_sprites,
+                      const int32_t* sprite_ids, const orc_color* palette, orc_pixel* gbuf,
+                      int32_t* texel, int row0, int row1, orc_counters* ctr) {
+    atlas_store st;
+    if (atlas_from_sprites(atlas, n_sprites, &st)) return -1;
+    trace_primary_atlas(v, count, bin_box, bin_ent, &st.a, sprite_ids, palette, gbuf, texel, row0, row1, ctr);
+    atlas_free(&st);
     return 0;
 }
 

@@ -35,6 +35,12 @@ class View(C.Structure):
     _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("L", C.c_int32)]
 
 
+class Atlas(C.Structure):
+    """orc_atlas: sprites of per-entry width x height, concatenated tables."""
+    _fields_ = [("n", C.c_int32), ("w", C.c_void_p), ("h", C.c_void_p), ("off", C.c_void_p),
+                ("color", C.c_void_p), ("depth", C.c_void_p), ("normal", C.c_void_p)]
+
+
 class Counters(C.Structure):
     _fields_ = [(f, C.c_uint64) for f in COUNTER_FIELDS]
 
@@ -71,8 +77,12 @@ def lib():
         L.orc_script_c_key.argtypes = [C.c_int]
         L.orc_script_c_key.restype = C.c_int
         L.orc_grid_build.argtypes = [C.POINTER(View), vp, C.c_int, vp, vp, vp]
-        L.orc_trace_primary.argtypes = [C.POINTER(View), vp, vp, vp, vp, vp, vp, vp, vp, C.c_int,
+        L.orc_trace_primary.argtypes = [C.POINTER(View), vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int,
                                         C.c_int, C.POINTER(Counters)]
+        L.orc_trace_primary.restype = C.c_int
+        L.orc_render_frame_atlas.argtypes = [C.POINTER(View), vp, vp, C.c_int, C.POINTER(Atlas), vp, vp, C.c_int,
+                                             vp, vp, vp, C.c_int, C.c_int, C.POINTER(Counters), C.c_int, vp, vp]
+        L.orc_render_frame_atlas.restype = C.c_int
         L.orc_shade.argtypes = [C.POINTER(View), vp, vp, vp, vp, vp, C.c_int, vp, C.c_int,
                                 C.c_int, C.POINTER(Counters)]
         L.orc_draw_overlay.argtypes = [C.POINTER(View), vp, vp, C.c_int, C.c_int, vp]
@@ -150,12 +160,33 @@ def grid_build(W, H, L, boxes):
     return count, bin_box, bin_ent
 
 
+def ragged_atlas(sprites):
+    """[(color (h,w) int, depth (h,w) int, normal (h,w,3) float), ...] -> the five arrays of an
+    orc_atlas / par_set_atlas_sized: w, h, color, depth, normal (concatenated, row-major)."""
+    w = np.array([s[0].shape[1] for s in sprites], np.int32)
+    h = np.array([s[0].shape[0] for s in sprites], np.int32)
+    color = np.concatenate([np.asarray(s[0], np.int32).reshape(-1) for s in sprites])
+    depth = np.concatenate([np.asarray(s[1], np.int32).reshape(-1) for s in sprites])
+    normal = np.concatenate([np.asarray(s[2], np.float32).reshape(-1, 3) for s in sprites])
+    return w, h, np.ascontiguousarray(color), np.ascontiguousarray(depth), np.ascontiguousarray(normal)
+
+
 def render(W, H, L, boxes, lights, atlas=None, palette=None, sprite_ids=None, row0=0, row1=None,
-           want_rgba=True, want_gbuf=True, want_texel=True, threads=None):
+           want_rgba=True, want_gbuf=True, want_texel=True, threads=None, sized_atlas=None,
+           dbg_light=None):
     """One frame (alternative.cpp:689-760, no overlay).  Returns a dict with rgba (H,W) COLOR,
     gbuf (H,W) PIXEL, texel (H,W) int32 and the §8(d) counters; only rows [row0,row1) are
-    rendered (the rest stay zero)."""
-    atlas = tile_floor() if atlas is None else atlas
+    rendered (the rest stay zero).  sized_atlas = (w, h, color, depth, normal) from ragged_atlas()
+    replaces the fixed 20x40 `atlas`; dbg_light = l adds 't' (H,W,4: t.xyz, Lambert term of light l)
+    and 'factor' (H,W: acc + ambient) — the fp32 intermediates."""
+    if sized_atlas is None:
+        atlas = tile_floor() if atlas is None else atlas
+        sized_atlas = ragged_atlas([(sp["color"].reshape(40, 20), sp["depth"].reshape(40, 20),
+                                     sp["normal"].reshape(40, 20, 3)) for sp in atlas])
+    aw, ah, acolor, adepth, anormal = sized_atlas
+    aoff = np.concatenate([[0], np.cumsum(aw.astype(np.int64) * ah)[:-1]]).astype(np.int32)
+    at = Atlas(len(aw), aw.ctypes.data, ah.ctypes.data, aoff.ctypes.data, acolor.ctypes.data,
+               adepth.ctypes.data, anormal.ctypes.data)
     palette = default_palette() if palette is None else palette
     row1 = H if row1 is None else row1
     v = View(W, H, L)
@@ -168,15 +199,18 @@ def render(W, H, L, boxes, lights, atlas=None, palette=None, sprite_ids=None, ro
     old = os.environ.get("OMP_NUM_THREADS")
     if threads is not None:
         _omp_set_threads(threads)
-    rc = lib().orc_render_frame(C.byref(v), _p(boxes), _p(sprite_ids), len(boxes), _p(atlas),
-                                _p(palette), _p(lights), len(lights), _p(rgba), _p(gbuf),
-                                _p(texel), row0, row1, C.byref(ctr))
+    dbg_t = np.zeros((H, W, 4), np.float32) if dbg_light is not None else None
+    dbg_f = np.zeros((H, W), np.float32) if dbg_light is not None else None
+    rc = lib().orc_render_frame_atlas(C.byref(v), _p(boxes), _p(sprite_ids), len(boxes), C.byref(at),
+                                      _p(palette), _p(lights), len(lights), _p(rgba), _p(gbuf),
+                                      _p(texel), row0, row1, C.byref(ctr),
+                                      -1 if dbg_light is None else int(dbg_light), _p(dbg_t), _p(dbg_f))
     if threads is not None:
         _omp_set_threads(0 if old is None else int(old))
     if rc != 0:
         raise MemoryError("orc_render_frame")
     return {"rgba": rgba, "gbuf": gbuf, "texel": texel, "counters": ctr.as_dict(),
-            "ops": lib().orc_algorithmic_ops(C.byref(ctr))}
+            "ops": lib().orc_algorithmic_ops(C.byref(ctr)), "t": dbg_t, "factor": dbg_f}
 
 
 def _omp_set_threads(n: int) -> None:

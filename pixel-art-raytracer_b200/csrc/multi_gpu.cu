@@ -54,6 +54,15 @@ struct Nccl {
 Nccl g_nccl;
 thread_local char g_multi_err[256] = "";
 
+// Restores the caller's current device on every exit path.
+struct DeviceScope {
+    int prev = -1;
+    DeviceScope() { cudaGetDevice(&prev); }
+    ~DeviceScope() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 }  // namespace
 
 struct par_multi {
@@ -179,12 +188,19 @@ int par_multi_create(par_multi** out, const par_config* cfg, const int* devices,
 int par_multi_size(const par_multi* m) { return m ? m->n : 0; }
 par_ctx* par_multi_context(par_multi* m, int i) { return (m && i >= 0 && i < m->n) ? m->ctx[i] : nullptr; }
 
+// On an error every device is drained before returning, so that no device keeps work in flight on
+// state the others never received (the caller re-sends atlas / scene after an error).
+static int drain_and_return(par_multi* m, int rc) {
+    for (int i = 0; i < m->n; i++) par_sync(m->ctx[i]);
+    return rc;
+}
+
 int par_multi_set_atlas(par_multi* m, const par_sprite* sprites, int n_sprites, const par_color* palette,
                         int n_palette) {
     if (!m) return PAR_ERR_INVALID_ARG;
     for (int i = 0; i < m->n; i++) {
         int rc = par_set_atlas(m->ctx[i], sprites, n_sprites, palette, n_palette);
-        if (rc != PAR_OK) return rc;
+        if (rc != PAR_OK) return drain_and_return(m, rc);
     }
     return PAR_OK;
 }
@@ -193,7 +209,7 @@ int par_multi_set_scene(par_multi* m, const par_aabb* aabbs, const int32_t* spri
     if (!m) return PAR_ERR_INVALID_ARG;
     for (int i = 0; i < m->n; i++) {  // asynchronous per device: uploads and loaders overlap
         int rc = par_set_scene(m->ctx[i], aabbs, sprite_ids, n);
-        if (rc != PAR_OK) return rc;
+        if (rc != PAR_OK) return drain_and_return(m, rc);
     }
     return PAR_OK;
 }
@@ -202,6 +218,7 @@ int par_multi_set_scene(par_multi* m, const par_aabb* aabbs, const int32_t* spri
 int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_color* out_rgba, par_stats* stats) {
     g_multi_err[0] = 0;
     if (!m) return PAR_ERR_INVALID_ARG;
+    DeviceScope scope;  // the caller's current device is restored on every exit
     if (m->n == 1) {
         int rc = par_render_device(m->ctx[0], lights, n_lights, nullptr);
         if (rc != PAR_OK) return rc;
@@ -212,27 +229,32 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
         for (int i = 0; i < m->n; i++) {
             int rc = par_render_device(m->ctx[i], lights, n_lights, nullptr);
             if (rc == PAR_OK) rc = par_read_stripes(m->ctx[i], out_rgba);
-            if (rc != PAR_OK) return rc;
+            if (rc != PAR_OK) return drain_and_return(m, rc);
         }
     } else if (m->peer) {
-        int prev = 0;
-        cudaGetDevice(&prev);
         for (int i = 0; i < m->n; i++) {  // asynchronous: all devices render and scatter concurrently
             int rc = par_render_device_peers(m->ctx[i], lights, n_lights);
-            if (rc != PAR_OK) return rc;
-            cudaSetDevice(m->device[i]);
-            cudaEventRecord(m->done[i], static_cast<cudaStream_t>(par_get_stream(m->ctx[i])));
+            if (rc != PAR_OK) return drain_and_return(m, rc);
+            cudaError_t e = cudaSetDevice(m->device[i]);
+            if (e == cudaSuccess) e = cudaEventRecord(m->done[i], static_cast<cudaStream_t>(par_get_stream(m->ctx[i])));
+            if (e != cudaSuccess) {
+                snprintf(g_multi_err, sizeof g_multi_err, "par_multi_render: %s", cudaGetErrorString(e));
+                return drain_and_return(m, PAR_ERR_CUDA);
+            }
         }
         for (int i = 0; i < m->n; i++) {  // a frame is complete once EVERY device has finished writing into it
-            cudaSetDevice(m->device[i]);
-            for (int j = 0; j < m->n; j++)
-                if (j != i) cudaStreamWaitEvent(static_cast<cudaStream_t>(par_get_stream(m->ctx[i])), m->done[j], 0);
+            cudaError_t e = cudaSetDevice(m->device[i]);
+            for (int j = 0; j < m->n && e == cudaSuccess; j++)
+                if (j != i) e = cudaStreamWaitEvent(static_cast<cudaStream_t>(par_get_stream(m->ctx[i])), m->done[j], 0);
+            if (e != cudaSuccess) {
+                snprintf(g_multi_err, sizeof g_multi_err, "par_multi_render: %s", cudaGetErrorString(e));
+                return drain_and_return(m, PAR_ERR_CUDA);
+            }
         }
-        cudaSetDevice(prev);
     } else {
         for (int i = 0; i < m->n; i++) {  // asynchronous: all devices render their stripes concurrently
             int rc = par_render_device_striped(m->ctx[i], lights, n_lights, m->staging[i]);
-            if (rc != PAR_OK) return rc;
+            if (rc != PAR_OK) return drain_and_return(m, rc);
         }
         const size_t block = par_staging_bytes(m->ctx[0]) / m->n;  // one rank's contiguous stripes
         ncclResult_t r = g_nccl.GroupStart();
@@ -245,7 +267,7 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
         if (r == ncclSuccess) r = e;
         if (r != ncclSuccess) {
             snprintf(g_multi_err, sizeof g_multi_err, "NCCL frame gather: %s", g_nccl.GetErrorString(r));
-            return PAR_ERR_NCCL;
+            return drain_and_return(m, PAR_ERR_NCCL);
         }
         for (int i = 0; i < m->n; i++) {  // staging -> raster frame on every device
             int rc = par_unstripe_device(m->ctx[i], m->staging[i], par_device_frame(m->ctx[i]));
@@ -263,8 +285,7 @@ int par_multi_render(par_multi* m, const par_light* lights, int n_lights, par_co
             par_stats s;
             if (par_get_stats(m->ctx[i], &s) != PAR_OK) continue;
             if (s.ms_total > stats->ms_total) stats->ms_total = s.ms_total;
-            if (s.ms_shade > stats->ms_shade) stats->ms_shade = s.ms_shade;
-            if (s.ms_primary > stats->ms_primary) stats->ms_primary = s.ms_primary;
+            if (s.ms_render > stats->ms_render) stats->ms_render = s.ms_render;
             stats->kernel_launches += s.kernel_launches;
             stats->rays += s.rays;
         }

@@ -1,5 +1,5 @@
-// par_kernels.cuh — parameter blocks and host-side launchers of the three kernel groups
-// (scene_loader.cu, primary.cu, shade.cu); shared with the C ABI layer (par_api.cu).
+// par_kernels.cuh — parameter blocks and host-side launchers of the kernel groups
+// (scene_loader.cu, tile.cu); shared with the C ABI layer (par_api.cu).
 #pragma once
 #include "par_device.cuh"
 
@@ -9,88 +9,99 @@ namespace par {
 struct LoaderCounters {
     int n_survivors;
     int n_inserts;
-    int reserved;
-    int bad_scene;  // set when an AABB would index outside the 20x40 sprite (quirk Q7)
-};
-cudaError_t launch_scene_loader(const int4* raw, const int* sprite_ids, int n, int n_sprites,
-                                const ViewDims& d, int4* boxes, int* cnt, int* ids,
-                                unsigned* occ4, int* survivors, LoaderCounters* ctr,
-                                LoaderCounters* host_a, LoaderCounters* host_b,
-                                cudaStream_t s, int* launches);
-
-// ---- per-tile shadow-walk work descriptors (primary -> walks -> shade) ----
-constexpr int kMaxGroups = 24;    // z-groups per tile with precomputed walks (more: shade walks itself)
-constexpr int kWalkListCap = 16;  // boxes kept per (tile, group, light) list in the pool
-struct GroupMeta {                // one z-group of a tile: all its pixels start their shadow walk in
-    int z;                        //   bin (tile x, tile y, z)  (alternative.cpp:724-727, quirk Q11)
-    int npix;
-    int omin[3], omax[3];         // integer bounds of the group's ray origins (alternative.cpp:720-722)
+    int bad_entity;  // first (lowest) entity whose box would index outside its sprite, or INT_MAX
+    int bad_scene;   // set when an inserted AABB would index outside its sprite (quirk Q7)
+    int n_list;      // entries of the survivor list (>= n_survivors: moved entities are appended)
+    int blocks_done; // grid-wide completion counter of the occupancy pass
+    int pad[2];
 };
 
-// ---- primary rays (alternative.cpp:271-383) ----
-struct PrimaryParams {
+// One generation of the view-hash grid.  Two generations alternate: while frame k
+// is built into one, the bins the other one's survivors touched are cleared in the same launch.
+struct GridBuffers {
+    int* cnt;         // [V]   inserts per bin (the reference's wrapping count is cnt & 7)
+    int* ids;         // [V*8] the <= 7 highest inserting entity ids per bin, descending; -1 = empty
+    unsigned* occ4;   // 4 bits per bin: cnt & 7
+    int4* boxes;      // [cap] packed box records this grid was built from (.w = sprite id)
+    int* survivors;   // [cap] entities inserted into this grid (clear list for its next reuse)
+    LoaderCounters* ctr;
+};
+
+struct LoaderParams {
     ViewDims d;
-    const int* cnt;
-    const int* ids;
-    const int4* boxes;
-    const int* atlas_depth;  // [n_sprites][800]
-    int n_sprites;
-    int4* gbuf;
-    int tile_row_first;  // first owned tile row (bin_y); the next ones are stripe_n apart
-    int* tile_ngroups;   // [HW*HH]: z-groups of the tile (ascending z), -1 = more than kMaxGroups
-    GroupMeta* groups;   // [HW*HH][kMaxGroups]
+    const int4* raw;         // uploaded AABB records (alternative.cpp:35-38)
+    const int* sprite_ids;   // optional
+    const int2* sprite_dims; // [n_sprites]: texel base, width | height << 16
+    int n, n_sprites;
+    GridBuffers cur;         // built by this launch
+    GridBuffers old;         // its touched bins are cleared by this launch (old.cnt == NULL: nothing to clear)
+    int old_n_list_cap;      // upper bound of old's survivor list (threads to spend on the clear)
+    LoaderCounters* host_a;  // page-locked host copies of the counters (either may be NULL)
+    LoaderCounters* host_b;
 };
-size_t primary_smem_bytes(const ViewDims& d, int n_sprites);
-cudaError_t configure_primary(size_t smem);  // per device, before the first launch
-cudaError_t launch_primary(const PrimaryParams& p, cudaStream_t s);
+cudaError_t launch_scene_loader(const LoaderParams& p, cudaStream_t s, int* launches);
+// Whole-grid clear (context creation / recovery): insert totals 0, slots -1, occupancy 0, counters 0.
+cudaError_t launch_clear_grid(const GridBuffers& g, int V, cudaStream_t s);
 
-// ---- shadow walks (alternative.cpp:399-476 minus the slab tests): one warp per (tile, group, light) ----
-struct WalkParams {
+// Incremental update (alternative.cpp:641-681: only entity 0 and light 0 ever move): entities
+// [first, first + count) get new boxes; only the bins their old and new boxes span are rebuilt.
+constexpr int kMaxUpdate = 8;  // entities per incremental update (more: full rebuild)
+struct UpdateParams {
     ViewDims d;
-    const int* ids;
-    const unsigned* occ4;
-    const int4* boxes;
-    const int* tile_ngroups;
-    const GroupMeta* groups;
-    int2* table;       // [HW*HH][kMaxGroups][n_lights]: (pool offset, box count) or count -1 = not available
-    int4* pool;        // kept boxes: .x.y.z = the packed 16-bit box record, .w = entity index
-    int* pool_cursor;
-    int pool_cap;
-    int n_lights;
-    int tile_row_first;
-    int debug_flags;
-    short4 lights[64];
+    GridBuffers g;
+    const int2* sprite_dims;
+    int n, n_sprites;
+    int count;                   // updated entities
+    int first;                   // index of the first one
+    int4 fresh[kMaxUpdate];      // their new packed records (.w = sprite id)
+    int keep_sprite_ids;         // 1: .w of fresh is ignored, the entities keep their sprites
+    int4* raw;                   // the resident upload buffer is kept in step (later full re-bins read it)
+    int* raw_sprite_ids;         // likewise (may be NULL)
+    LoaderCounters* host_a;
+    LoaderCounters* host_b;
 };
-cudaError_t launch_walks(const WalkParams& p, cudaStream_t s);
+cudaError_t launch_scene_update(const UpdateParams& p, cudaStream_t s, int* launches);
+cudaError_t launch_publish_counters(const GridBuffers& g, LoaderCounters* host_a, LoaderCounters* host_b, cudaStream_t s);
+size_t loader_counter_bytes();  // LoaderCounters + the update scratch that lives right behind them
 
-// ---- shading + shadow rays + RGBA8 pack (alternative.cpp:702-760, 399-500, 40-83) ----
+// ---- the render kernel: primary rays + shading + shadow rays + RGBA8 pack, one CTA per tile
+//      (alternative.cpp:271-383, 702-760, 399-500, 40-83) ----
+constexpr int kTileCtaThreads = 160;
 constexpr int kMaxLights = 64;
-struct ShadeParams {
+struct TileParams {
     ViewDims d;
     const int* cnt;
     const int* ids;
     const unsigned* occ4;      // 4 bits per bin: cnt & 7 (8 bins per word)
     const int4* boxes;
-    const int4* gbuf;
-    const float* atlas_normal;         // [n_sprites][800][3]
-    const unsigned char* atlas_color;  // [n_sprites][800] palette index
-    const uchar4* palette;
-    uchar4* out;  // full frame, W*H
+    const int* atlas_depth;    // [atlas_texels] depth offsets (sprites.hpp:69)
+    const float4* texel_tab;   // [atlas_texels] normal.xyz (sprites.hpp:70) + palette colour of the texel (RGBA8 bits in .w)
+    const int2* sprite_dims;   // [n_sprites]: texel base, width | height << 16
+    int atlas_texels;
+    uchar4* out;               // full frame, W*H
+    int4* gbuf;                // optional parity checkpoint: entity, y, z, global texel index (-1 = miss)
+    int gbuf_only;             // 1: primary rays only (par_get_gbuffer after a frame rendered without gbuf)
     int n_lights;
     float ambient;
-    int tile_row_first;
-    int out_stripe_T;  // 0: raster output; T > 0: stripe-major staging, T stripes per rank
-    int n_peer_out;    // fused frame exchange: every finished 16-byte chunk is also stored, in place, into
-    uchar4* peer_out[7];  //   the raster frames of the other GPUs (peer memory over NVLink / NVSwitch)
-    int debug_flags;   // bit 0: disable the shaft cull, bit 2: ignore precomputed walks (A/B measurements only)
-    const int* tile_ngroups;  // precomputed walks (walks.cu); NULL = shade walks itself
-    const int2* table;
-    const int4* pool;
+    int tile_row_first;        // first owned tile row (bin_y); the next ones are stripe_n apart
+    int out_stripe_T;          // 0: raster output; T > 0: stripe-major staging, T stripes per rank
+    int n_peer_out;            // fused frame exchange: every finished 16-byte chunk is also stored, in place, into
+    uchar4* peer_out[7];       //   the raster frames of the other GPUs (peer memory over NVLink / NVSwitch)
+    const int* tile_order;     // optional: CTA -> tile slot (longest-first order of the previous frame's costs)
+    unsigned* tile_cost;       // optional: cycles per tile, indexed ty * HW + bx
+    int probe_x, probe_y;      // cursor probe pixel (-1: off) and where its 28-byte record goes (mapped host memory)
+    int* probe_a;
+    int* probe_b;
+    int debug_flags;           // bit 0: disable the shaft cull (A/B measurements and tests only)
     unsigned long long* phase_cycles;  // optional debug instrumentation: 16 counters (NULL in production)
-    short4 lights[kMaxLights];         // x, y, z, radius (alternative.cpp:619-622)
+    int dbg_light;             // optional export of fp32 intermediates: t.xyz + Lambert term of this light
+    float4* dbg_t;             //   [W*H]
+    float* dbg_factor;         //   [W*H] acc + ambient
+    short4 lights[kMaxLights]; // x, y, z, radius (alternative.cpp:619-622)
 };
-size_t shade_smem_bytes();
-cudaError_t configure_shade();  // per device, before the first launch
-cudaError_t launch_shade(const ShadeParams& p, cudaStream_t s);
+size_t tile_smem_bytes();
+cudaError_t configure_tile();  // per device, before the first launch
+cudaError_t launch_tile(const TileParams& p, cudaStream_t s);
+cudaError_t launch_tile_order(const unsigned* cost, int* order, const ViewDims& d, cudaStream_t s);
 
 }  // namespace par

@@ -1,0 +1,1001 @@
+// tile.cu — the render kernel: ONE CTA per 40x40 screen tile does the whole per-pixel path of
+// the reference frame loop for that tile,
+//     trace_hash_for_pixel           /root/reference/src/alternative.cpp:271-383   (phase P)
+//     shading loop                   alternative.cpp:702-760                       (phases G, R)
+//     trace_hash_for_light           alternative.cpp:399-500
+//     AABB::intersect                alternative.cpp:40-83
+//     Vector::normalize, Color::operator*   sprites.hpp:28-35, 8-16
+// generalised to N lights:  acc = sum over visible lights of max(0, n . t_l);
+// out = color * min(1, acc + ambient).
+//
+// Why one kernel: a 40x40 tile is one column of bins for the primary rays AND the unit that shares
+// shadow-ray grid walks, so the G-buffer record of a pixel (entity, z, texel) never has to leave the
+// SM: it goes from the registers of phase P into 10 bytes of shared memory and is consumed there.
+// The 16-byte-per-pixel G-buffer in HBM is written only when a caller asks for the parity
+// checkpoint (par_render(out_gbuf), par_get_gbuffer).
+//
+//   P  primary rays (integer only).  The column's occupied bins are scanned and their entries
+//      gathered into shared memory in the reference's (bin_z, slot) order, pre-digested into the
+//      integers the per-pixel test needs (chunks of 256 entries).  A thread owns 10 pixels of ONE
+//      screen column (rows 4 apart) and walks the list for 5 of them at a time: 2-D integer hit test
+//      (quirk Q6), texel index with the sprite's own width (Q7 lifted), strict-greater depth select
+//      (Q8), two-adjacent-bins early-out with empty-bin reset (Q9), miss pixel (Q10), record (Q11).
+//   G  grouping.  Every hit pixel starts its shadow walks in bin (tile x, tile y, z / 40) (Q11) and
+//      the probed-bin sequence of a walk depends only on (start bin, light bin): pixels are
+//      counting-sorted by z / 40 into dense per-group lists (all groups of the tile at once; warp
+//      ballots + redux aggregate the shared-memory atomics), with the integer bounds of each
+//      group's ray origins for the shaft cull.
+//   R  rounds over (group, light) segments, up to 32 per round:
+//        walk    one thread per run of steps: the fp32 position chain is accumulated sequentially
+//                exactly as the reference does (Q15); the 7 probes of a step collapse to the
+//                distinct bins among them; 4-bit counts fetched as batches of independent loads;
+//        gather  a warp scan expands the occupied bins into dense (bin, slot) lanes: entity ->
+//                de-duplicate per segment (shared hash set; testing a box twice cannot change an
+//                OR) -> box -> shaft cull (shaft.cuh) -> float corners in the segment's share of a
+//                shared box list;
+//        shade   one lane per pixel of the round's groups: per light the L1-normalised direction
+//                (Q12), the Lambert term and — only when it is > 0 (Q19) — the slab tests of that
+//                segment's boxes with unbounded-line semantics (Q14), self-entity skip (Q17) and
+//                std::min/std::max NaN semantics (Q13) reproduced exactly (three variants, see
+//                slab_hit_*).  Rounds that do not fit the shared lists are split (fewer segments,
+//                then fewer steps of one light); the (acc, shadowed) state of an unfinished pixel
+//                is parked in its own slot of the output frame.
+//   Finished RGBA8 pixels are staged in shared memory and leave as 16-byte stores — into the own
+//   frame and, fused frame exchange, in place into the frames of peer GPUs over NVLink.
+// All fp32 arithmetic is IEEE round-to-nearest with no FMA contraction (-fmad=false).
+#include <climits>
+
+#include "par/par.h"
+#include "par_kernels.cuh"
+#include "shaft.cuh"
+
+namespace par {
+
+#ifndef PAR_TILE_MIN_CTAS
+#define PAR_TILE_MIN_CTAS 5
+#endif
+#ifndef PAR_TILE_LIST_CAP
+#define PAR_TILE_LIST_CAP 448
+#endif
+namespace {
+
+constexpr int kT = kTileCtaThreads;             // 160 threads: 40 columns x 4 row phases
+constexpr int kPix = kBin * kBin;               // 1600 pixels per tile
+constexpr int kPPT = kPix / kT;                 // 10 pixels per thread (rows rsub + 4m)
+constexpr int kHalf = kPPT / 2;                 // pixels per primary pass
+constexpr int kListCap = PAR_TILE_LIST_CAP;     // boxes in the shared list (two float4 each)
+constexpr int kHashBits = 10;
+constexpr int kHashSize = 1 << kHashBits;       // de-duplication set
+constexpr int kOccCap = 512;                    // occupied bins found by the walks of one round
+constexpr int kSegMax = 32;                     // (group, light, step range) segments per round
+constexpr int kGroupMax = 64;                   // z-groups handled per pass over the tile
+constexpr int kEntryCap = 256;                  // column entries staged at a time (phase P)
+constexpr int kMaxRun = 32;                     // most walk steps per walk-phase thread
+constexpr int kMaxHL = PAR_MAX_VIEW / kBin;     // 320 bins along z at most
+constexpr int kWarps = kT / 32;
+constexpr int kNoGroup = INT_MAX;
+constexpr unsigned kEmpty = 0xffffffffu;
+static_assert(kPix % kT == 0 && kT % 32 == 0 && kT % kBin == 0 && kPPT % 2 == 0, "CTA shape");
+static_assert(kHashSize * 3 / 4 >= kListCap, "the hash set must hold a full list");
+
+struct Seg {
+    float sx, sy, sz;  // bin_step_size (alternative.cpp:423-425)
+    int light;         // index into TileParams::lights
+    int grp;           // index into TileSmem::grp
+    int start;         // flat index of the start bin (quirk Q16)
+    int steps;         // (int)largest_bin_distance of the whole walk
+    int ka, kb;        // step range [ka, kb) covered by this segment
+    int item0;         // first walk-phase work item
+    int count;         // boxes found (before de-duplication)
+    int base;          // first slot of the segment in the box list
+    int fill;          // boxes stored (after de-duplication and cull)
+    int octant;        // >= 0: every ray of the group has this sign octant (bit a = component a negative) and
+                       // the boxes are stored as (near, far) corners; -1: mixed, boxes stored as (lo, hi)
+};
+
+struct Grp {
+    int gz;                  // start-bin z of the group = world z / 40 (ray_bin_z, alternative.cpp:727)
+    int n;                   // pixels
+    int p0;                  // first slot in TileSmem::pix
+    int omin[3], omax[3];    // integer bounds of the group's ray origins (alternative.cpp:720-722)
+};
+
+struct RoundSmem {  // phases G/R
+    float4 list[2 * kListCap];
+    unsigned hash[kHashSize];
+    unsigned occ_bin[kOccCap];       // flat bin
+    unsigned char occ_meta[kOccCap]; // segment << 3 | count
+};
+struct PrimarySmem {  // phase P (aliases RoundSmem)
+    int cnt[kMaxHL];
+    int off[kMaxHL + 1];
+    int4 A[kEntryCap];  // x0, x1 (exclusive), lo = py+pz, top = py+ey+pz+ez
+    int4 B[kEntryCap];  // key0 = py-pz, ey, pz, texel base of the sprite
+    int2 C[kEntryCap];  // entity, width << 2 | gap << 1 | first
+};
+constexpr int kStageTexels = (int)((sizeof(RoundSmem) - sizeof(PrimarySmem)) / sizeof(int));
+static_assert(sizeof(PrimarySmem) + 800 * sizeof(int) <= sizeof(RoundSmem), "the 20x40 sprite's depths must fit");
+
+struct TileSmem {
+    union {
+        RoundSmem r;
+        struct {
+            PrimarySmem p;
+            int depth[kStageTexels];
+        } pp;
+    };
+    int ent[kPix];            // hit entity (quirk Q17 needs it)
+    unsigned w[kPix];         // global texel index of the hit; becomes the finished RGBA8 pixel
+    short z[kPix];            // world z of the hit (fits: see par_set_atlas_sized)
+    unsigned short pix[kPix]; // pixel indices sorted by group
+    Grp grp[kGroupMax];
+    int cursor[kGroupMax];
+    Seg seg[kSegMax];
+    unsigned bits[2];
+    int gmin;
+    int n_occ;
+    int overflow;
+    int n_items;
+    int run;
+};
+
+constexpr int kScratchRows = (int)(sizeof(float4) * 2 * kListCap / sizeof(int) / kT);
+static_assert(kScratchRows >= 14, "scratch too small for two walk steps");
+
+// alternative.cpp:40-83, literal std::min/std::max (valid for every input, NaN included).
+__device__ __forceinline__ bool slab_hit_exact(const float4 lo, const float4 hi, float ox, float oy,
+                                               float oz, float ix, float iy, float iz) {
+    // (float)(int - int) of 16-bit operands equals the float difference exactly, so the
+    // reference's int subtract + convert is one FADD here.
+    float x1 = (lo.x - ox) * ix, x2 = (hi.x - ox) * ix;
+    float tmin = std_min(x1, x2);
+    float tmax = std_max(x1, x2);
+    float y1 = (lo.y - oy) * iy, y2 = (hi.y - oy) * iy;
+    tmin = std_max(tmin, std_min(y1, y2));
+    tmax = std_min(tmax, std_max(y1, y2));
+    float z1 = (lo.z - oz) * iz, z2 = (hi.z - oz) * iz;
+    tmin = std_max(tmin, std_min(z1, z2));
+    tmax = std_min(tmax, std_max(z1, z2));
+    return tmax >= tmin;
+}
+
+// Same test when no operand can be NaN (finite non-zero direction => finite products): then
+// std::min/std::max and fminf/fmaxf agree up to the sign of zero, which no comparison sees.
+__device__ __forceinline__ bool slab_hit_fast(const float4 lo, const float4 hi, float ox, float oy,
+                                              float oz, float ix, float iy, float iz) {
+    float x1 = (lo.x - ox) * ix, x2 = (hi.x - ox) * ix;
+    float y1 = (lo.y - oy) * iy, y2 = (hi.y - oy) * iy;
+    float z1 = (lo.z - oz) * iz, z2 = (hi.z - oz) * iz;
+    float tmin = fmaxf(fmaxf(fminf(x1, x2), fminf(y1, y2)), fminf(z1, z2));
+    float tmax = fminf(fminf(fmaxf(x1, x2), fmaxf(y1, y2)), fmaxf(z1, z2));
+    return tmax >= tmin;
+}
+
+// Same test again when, in addition, the signs of the three inverse-direction components are the
+// same for every pixel of the group (the light lies strictly outside the group's origin bounds
+// on every axis).  With lo <= hi, subtraction and a multiplication by a constant are monotonic in
+// fp32, so min(x1,x2) IS the product of the near corner (lo for a positive component, hi for a
+// negative one) and max(x1,x2) that of the far corner: the six inner min/max disappear.  The
+// gather stores the box as (near, far) corners for such a segment, so one code path serves all
+// eight sign octants: 6 FADD + 6 FMUL + 2 FMNMX3 per box.
+__device__ __forceinline__ bool slab_hit_near_far(const float4 nr, const float4 fr, float ox, float oy,
+                                                  float oz, float ix, float iy, float iz) {
+    const float tmin = fmaxf(fmaxf((nr.x - ox) * ix, (nr.y - oy) * iy), (nr.z - oz) * iz);
+    const float tmax = fminf(fminf((fr.x - ox) * ix, (fr.y - oy) * iy), (fr.z - oz) * iz);
+    return tmax >= tmin;
+}
+
+// kMode 0: (near, far) storage, sign octant uniform; 1: NaN-free, (lo, hi) storage; 2: exact.
+template <int kMode>
+__device__ __forceinline__ bool any_box_hit(const float4* __restrict__ boxes, int n, int self,
+                                            float ox, float oy, float oz, float ix, float iy,
+                                            float iz) {
+#pragma unroll 1
+    for (int e = 0; e < n; e++) {
+        const float4 lo = boxes[2 * e], hi = boxes[2 * e + 1];
+        bool hit;
+        if (kMode == 2) hit = slab_hit_exact(lo, hi, ox, oy, oz, ix, iy, iz);
+        else if (kMode == 1) hit = slab_hit_fast(lo, hi, ox, oy, oz, ix, iy, iz);
+        else hit = slab_hit_near_far(lo, hi, ox, oy, oz, ix, iy, iz);
+        if (hit && __float_as_int(lo.w) != self) return true;  // quirk Q17: own entity never shadows
+    }
+    return false;
+}
+
+// Box -> shared list slot `at`: (lo, hi) corners, or (near, far) corners for a uniform sign octant.
+__device__ __forceinline__ void store_box(float4* list, int at, const Box& b, int ent, int octant) {
+    const float lx = (float)b.px, ly = (float)b.py, lz = (float)b.pz;
+    const float hx = (float)(b.px + b.ex), hy = (float)(b.py + b.ey), hz = (float)(b.pz + b.ez);
+    const bool sx = octant > 0 && (octant & 1), sy = octant > 0 && (octant & 2), sz = octant > 0 && (octant & 4);
+    list[2 * at] = make_float4(sx ? hx : lx, sy ? hy : ly, sz ? hz : lz, __int_as_float(ent));
+    list[2 * at + 1] = make_float4(sx ? lx : hx, sy ? ly : hy, sz ? lz : hz, 0.f);
+}
+
+// Sign octant shared by every ray of a group towards light lt, or -1.  Uses the measured integer
+// bounds of the group's origins; strict separation also guarantees that no direction component is
+// zero, i.e. that the NaN cases of quirk Q13 cannot occur for this (group, light).
+__device__ __forceinline__ int group_octant(const Grp& g, short4 lt) {
+    const int L[3] = {lt.x, lt.y, lt.z};
+    int oct = 0;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if (g.omin[a] < -32768 || g.omax[a] > 32767) return -1;  // origins are cast to short
+        if (L[a] < g.omin[a]) oct |= 1 << a;
+        else if (!(L[a] > g.omax[a])) return -1;
+    }
+    return oct;
+}
+
+__device__ __forceinline__ unsigned quantise(unsigned rgba, float f) {  // sprites.hpp:8-16
+    const unsigned r = (unsigned char)((float)(rgba & 255u) * f);
+    const unsigned g = (unsigned char)((float)((rgba >> 8) & 255u) * f);
+    const unsigned b = (unsigned char)((float)((rgba >> 16) & 255u) * f);
+    return r | g << 8 | b << 16 | (rgba & 0xff000000u);
+}
+
+constexpr unsigned kMissColor = 127u | 127u << 8 | 127u << 16;  // alternative.cpp:281, alpha 0
+
+}  // namespace
+
+__global__ void __launch_bounds__(kT, PAR_TILE_MIN_CTAS)
+k_tile(const __grid_constant__ TileParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileSmem& s = *reinterpret_cast<TileSmem*>(smem_raw);
+
+    const ViewDims& d = p.d;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const long long t_begin = p.tile_cost ? clock64() : 0;
+    const int slot = p.tile_order ? p.tile_order[blockIdx.x] : (int)blockIdx.x;
+    const int bx = slot % d.HW;
+    const int ty = p.tile_row_first + (slot / d.HW) * max(d.stripe_n, 1);
+    const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
+    const int n_lights = p.n_lights;
+    const int col = tid % kBin, rsub = tid / kBin;  // the thread's pixels: rows rsub + 4m of column col
+    const int i = bx * kBin + col;
+
+    // Optional barrier-to-barrier phase timing (debug; p.phase_cycles is NULL in production).
+    enum { kPhPrimary, kPhGroup, kPhSetup, kPhWalk, kPhGather, kPhShade, kPhTail };
+    long long t_mark = 0;
+    if (p.phase_cycles && tid == 0) t_mark = clock64();
+    auto mark = [&](int phase) {
+        if (p.phase_cycles && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(&p.phase_cycles[phase], (unsigned long long)(now - t_mark));
+            t_mark = now;
+        }
+    };
+
+    // =============================== P. primary rays ===============================
+    {
+        PrimarySmem& ps = s.pp.p;
+        const int col0 = flat_bin(d, bx, ty, 0);
+        // the column's counts (the reference's wrapping count is cnt & 7) and, for small atlases, the depth tables
+        for (int bz = tid; bz < d.HL; bz += kT) ps.cnt[bz] = __ldg(&p.cnt[col0 + bz]) & (kSlots - 1);
+        const bool staged = p.atlas_texels <= kStageTexels;
+        if (staged)
+            for (int t = tid; t < p.atlas_texels; t += kT) s.pp.depth[t] = __ldg(&p.atlas_depth[t]);
+        __syncthreads();
+        if (tid < 32) {  // exclusive scan over bin_z
+            int carry = 0;
+            for (int base = 0; base < d.HL; base += 32) {
+                const int bz = base + tid;
+                const int v = bz < d.HL ? ps.cnt[bz] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                if (bz < d.HL) ps.off[bz] = carry + incl - v;
+                carry += __shfl_sync(0xffffffffu, incl, 31);
+            }
+            if (tid == 0) ps.off[d.HL] = carry;
+        }
+        __syncthreads();
+        const int n_total = ps.off[d.HL];
+        const bool single = n_total <= kEntryCap;  // the whole column fits one chunk: stage it once
+
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            int best[kHalf], r_ent[kHalf], r_z[kHalf], r_w[kHalf], run[kHalf];
+            unsigned any_bits = 0, live = 0;  // bit m: has_intersected in the current bin / pixel still marching
+#pragma unroll
+            for (int m = 0; m < kHalf; m++) {
+                const int j = ty * kBin + rsub + 4 * (pass * kHalf + m);
+                best[m] = INT_MIN;  // closest_entity_depth, alternative.cpp:289
+                r_ent[m] = 0;       // miss pixel: entity 0, z 0 (quirk Q10)
+                r_z[m] = 0;
+                r_w[m] = -1;
+                run[m] = 0;         // intersected_bin_count
+                if (j >= ra && j < rb) live |= 1u << m;
+            }
+            const int wj0 = (short)(d.H - (ty * kBin + rsub + 4 * pass * kHalf));  // world_j of pixel m: wj0 - 4m (alternative.cpp:280)
+            int b0 = 0;
+#pragma unroll 1
+            while (b0 < d.HL && n_total > 0) {
+                int b1 = d.HL;
+                if (!single) {  // largest b1 with off[b1] - off[b0] <= kEntryCap (a bin holds <= 7 entries)
+                    b1 = b0 + 1;
+                    while (b1 < d.HL && ps.off[b1 + 1] - ps.off[b0] <= kEntryCap) b1++;
+                }
+                const int e0 = ps.off[b0], n = ps.off[b1] - e0;
+                if (!(single && pass == 1)) {
+                    if (!(pass == 0 && b0 == 0)) __syncthreads();  // everyone is done with the previous chunk
+                    // gather the chunk's entries in (bin_z ascending, slot ascending) order
+                    for (int t = tid; t < (b1 - b0) * kSlots; t += kT) {
+                        const int bz = b0 + (t >> 3), sl = t & 7, c = ps.cnt[bz];
+                        if (sl >= c) continue;
+                        const int ent = __ldg(&p.ids[(size_t)(col0 + bz) * kSlots + (c - 1 - sl)]);
+                        const Box b = unpack_box(__ldg(&p.boxes[ent]));
+                        const int2 dims = __ldg(&p.sprite_dims[b.sprite]);  // texel base, width | height << 16
+                        const int pos = ps.off[bz] - e0 + sl;
+                        ps.A[pos] = make_int4(b.px, b.px + b.ex, b.py + b.pz, b.py + b.ey + b.pz + b.ez);
+                        ps.B[pos] = make_int4(b.py - b.pz, b.ey, b.pz, dims.x);
+                        const int first = (sl == 0);
+                        const int gap = first && (bz == 0 || ps.cnt[bz - 1] == 0);  // an empty bin precedes this one
+                        ps.C[pos] = make_int2(ent, (dims.y & 0xffff) << 2 | gap << 1 | first);
+                    }
+                    __syncthreads();
+                }
+                // per-pixel walk: the entry list is traversed once per thread and pass; the x half of the
+                // hit test (quirk Q6) is shared by the thread's pixels (one screen column)
+                for (int k = 0; k < n && live; k++) {
+                    const int2 c = ps.C[k];
+                    if (c.y & 1) {  // first entry of a bin: close the previous bin (alternative.cpp:368-374)
+#pragma unroll
+                        for (int m = 0; m < kHalf; m++) {
+                            run[m] += (any_bits >> m) & 1;
+                            if (run[m] >= 2) live &= ~(1u << m);  // two adjacent hit bins end the march (quirk Q9)
+                            if (c.y & 2) run[m] = 0;              // an empty bin in between resets the run (298-300)
+                        }
+                        any_bits = 0;
+                        if (!live) break;
+                    }
+                    const int4 a = ps.A[k];
+                    if (i < a.x || i >= a.y) continue;  // x half of quirk Q6
+                    const int4 b = ps.B[k];
+                    const int width = c.y >> 2;
+#pragma unroll
+                    for (int m = 0; m < kHalf; m++) {
+                        const int wj = wj0 - 4 * m;
+                        if (!((live >> m) & 1) || !(wj > a.z && wj <= a.w)) continue;  // y half of Q6
+                        const int row = a.w - wj;
+                        const int idx = b.w + row * width + (i - a.x);  // quirk Q7 with the sprite's own width
+                        const int dep = staged ? s.pp.depth[idx] : __ldg(&p.atlas_depth[idx]);
+                        const int key = b.x + min(0, b.y - row) - dep;  // quirk Q8
+                        if (best[m] < key) {  // strict: ties keep the earlier (bin_z, slot)
+                            best[m] = key;
+                            r_ent[m] = c.x;
+                            r_z[m] = b.z + dep;  // quirk Q11; y = world_j - z
+                            r_w[m] = idx;
+                            any_bits |= 1u << m;
+                        }
+                    }
+                }
+                b0 = b1;
+            }
+            // records of this pass -> shared memory (and the parity checkpoints, when asked for)
+#pragma unroll
+            for (int m = 0; m < kHalf; m++) {
+                const int row = rsub + 4 * (pass * kHalf + m);
+                const int pidx = row * kBin + col, j = ty * kBin + row;
+                s.ent[pidx] = r_ent[m];
+                s.z[pidx] = (short)r_z[m];
+                s.w[pidx] = (unsigned)r_w[m];
+                if (j < ra || j >= rb) {
+                    s.w[pidx] = 0xfffffffeu;  // not rendered by this context
+                    continue;
+                }
+                const int y = r_w[m] >= 0 ? (wj0 - 4 * m) - r_z[m] : 0;
+                if (p.gbuf) p.gbuf[(size_t)j * d.W + i] = make_int4(r_ent[m], y, r_z[m], r_w[m]);
+                if (i == p.probe_x && j == p.probe_y) {  // cursor probe (mouse_pixel, alternative.cpp:380-382)
+                    float4 tx = make_float4(0.f, 0.f, 0.f, __uint_as_float(kMissColor));
+                    if (r_w[m] >= 0) tx = __ldg(&p.texel_tab[r_w[m]]);
+                    const int rec[7] = {__float_as_int(tx.x), __float_as_int(tx.y), __float_as_int(tx.z),
+                                        __float_as_int(tx.w), y, r_z[m], r_ent[m]};
+                    for (int k = 0; k < 7; k++) {
+                        if (p.probe_a) p.probe_a[k] = rec[k];
+                        if (p.probe_b) p.probe_b[k] = rec[k];
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();  // records complete; the staging area is free
+    mark(kPhPrimary);
+
+    // ---- miss pixels (and every pixel when there is no light) are final; group key of the others ----
+    int gz[kPPT];
+    const float amb_only = std_min(1.f, 0.f + p.ambient);
+#pragma unroll
+    for (int m = 0; m < kPPT; m++) {
+        const int pidx = (rsub + 4 * m) * kBin + col;
+        const unsigned w = s.w[pidx];
+        gz[m] = kNoGroup;
+        if (w == 0xfffffffeu) continue;
+        if (w == 0xffffffffu) {
+            s.w[pidx] = quantise(kMissColor, amb_only);
+        } else if (n_lights == 0 || p.gbuf_only) {
+            s.w[pidx] = quantise(__float_as_uint(__ldg(&p.texel_tab[w]).w), amb_only);
+        } else {
+            gz[m] = s.z[pidx] / kBin;  // ray_bin_z (alternative.cpp:727, C division truncates toward zero)
+        }
+    }
+
+    // =============================== G + R, kGroupMax groups at a time ===============================
+    int g_done = INT_MIN;  // groups <= g_done are finished
+#pragma unroll 1
+    for (;;) {
+        // ---- smallest unprocessed group ----
+        if (tid == 0) {
+            s.gmin = kNoGroup;
+            s.bits[0] = s.bits[1] = 0u;
+        }
+        __syncthreads();
+        int mine = kNoGroup;
+#pragma unroll
+        for (int m = 0; m < kPPT; m++)
+            if (gz[m] != kNoGroup && gz[m] > g_done) mine = min(mine, gz[m]);
+        mine = __reduce_min_sync(0xffffffffu, mine);
+        if (lane == 0 && mine != kNoGroup) atomicMin(&s.gmin, mine);
+        __syncthreads();
+        const int gmin = s.gmin;
+        if (gmin == kNoGroup) break;
+        // ---- the groups present in [gmin, gmin + 64) ----
+        {
+            unsigned b0 = 0u, b1 = 0u;
+#pragma unroll
+            for (int m = 0; m < kPPT; m++) {
+                if (gz[m] == kNoGroup || gz[m] <= g_done) continue;
+                const unsigned rel = (unsigned)(gz[m] - gmin);
+                if (rel < 32u) b0 |= 1u << rel;
+                else if (rel < 64u) b1 |= 1u << (rel - 32u);
+            }
+            b0 = __reduce_or_sync(0xffffffffu, b0);
+            b1 = __reduce_or_sync(0xffffffffu, b1);
+            if (lane == 0) {
+                if (b0) atomicOr(&s.bits[0], b0);
+                if (b1) atomicOr(&s.bits[1], b1);
+            }
+        }
+        __syncthreads();
+        const unsigned bits0 = s.bits[0], bits1 = s.bits[1];
+        const int n_groups = __popc(bits0) + __popc(bits1);
+        auto group_index = [&](int g) -> int {  // index of group g among the present ones, -1 if not in this pass
+            if (g == kNoGroup || g <= g_done) return -1;
+            const unsigned rel = (unsigned)(g - gmin);
+            if (rel < 32u) return __popc(bits0 & ((1u << rel) - 1u));
+            if (rel < 64u) return __popc(bits0) + __popc(bits1 & ((1u << (rel - 32u)) - 1u));
+            return -1;
+        };
+        if (tid < kGroupMax) {
+            const unsigned present = tid < 32 ? (bits0 >> tid) & 1u : (bits1 >> (tid - 32)) & 1u;
+            if (present) {
+                Grp& g = s.grp[group_index(gmin + tid)];
+                g.gz = gmin + tid;
+                g.n = 0;
+                g.omin[0] = g.omin[1] = g.omin[2] = INT_MAX;
+                g.omax[0] = g.omax[1] = g.omax[2] = INT_MIN;
+            }
+        }
+        __syncthreads();
+        // ---- pixels per group and bounds of the ray origins (alternative.cpp:720-722): per warp one
+        //      ballot per distinct group, redux for the bounds, one lane does the shared atomics ----
+        int gi[kPPT];
+#pragma unroll
+        for (int m = 0; m < kPPT; m++) {
+            gi[m] = group_index(gz[m]);
+            const int row = rsub + 4 * m, pidx = row * kBin + col;
+            const int zz = s.z[pidx];
+            // x = column, z from the record, y = world_j - z (quirk Q11: y + z == H - row)
+            const int o3[3] = {i, (short)(d.H - (ty * kBin + row)) - zz, zz};
+            unsigned todo = __ballot_sync(0xffffffffu, gi[m] >= 0);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int gl = __shfl_sync(0xffffffffu, gi[m], leader);
+                const unsigned mask = __ballot_sync(0xffffffffu, gi[m] == gl);
+                if (gi[m] == gl) {
+                    int lo3[3], hi3[3];
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        lo3[a] = __reduce_min_sync(mask, o3[a]);
+                        hi3[a] = __reduce_max_sync(mask, o3[a]);
+                    }
+                    if (lane == leader) {
+                        Grp& g = s.grp[gl];
+                        atomicAdd(&g.n, __popc(mask));
+#pragma unroll
+                        for (int a = 0; a < 3; a++) {
+                            atomicMin(&g.omin[a], lo3[a]);
+                            atomicMax(&g.omax[a], hi3[a]);
+                        }
+                    }
+                }
+                todo &= ~mask;
+            }
+        }
+        __syncthreads();
+        if (tid < 32) {  // exclusive scan of the group sizes (two groups per lane)
+            const int a = tid < n_groups ? s.grp[tid].n : 0, b = tid + 32 < n_groups ? s.grp[tid + 32].n : 0;
+            int ia = a, ib = b;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+                if (tid >= o) {
+                    ia += ta;
+                    ib += tb;
+                }
+            }
+            const int total_a = __shfl_sync(0xffffffffu, ia, 31);
+            if (tid < n_groups) s.grp[tid].p0 = s.cursor[tid] = ia - a;
+            if (tid + 32 < n_groups) s.grp[tid + 32].p0 = s.cursor[tid + 32] = total_a + ib - b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < kPPT; m++) {  // scatter the pixel indices into the per-group lists
+            unsigned todo = __ballot_sync(0xffffffffu, gi[m] >= 0);
+            while (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int gl = __shfl_sync(0xffffffffu, gi[m], leader);
+                const unsigned mask = __ballot_sync(0xffffffffu, gi[m] == gl);
+                int base = 0;
+                if (lane == leader) base = atomicAdd(&s.cursor[gl], __popc(mask));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (gi[m] == gl) s.pix[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)((rsub + 4 * m) * kBin + col);
+                todo &= ~mask;
+            }
+        }
+        // (the barrier at the top of the first round publishes pix and the group table)
+        mark(kPhGroup);
+
+        // ---- rounds over (group, light, step range) segments; segment index = group * n_lights + light ----
+        const int n_seg_total = n_groups * n_lights;
+        int s_cur = 0, ka_cur = 0;  // next unprocessed step of segment s_cur
+        int kb_try = -1;            // trial end of the first segment (-1 = the whole walk)
+        int nseg_try = kSegMax;
+#pragma unroll 1
+        while (s_cur < n_seg_total) {
+            __syncthreads();  // previous round fully consumed (lists, segments, pixel lists complete)
+            // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
+            const int nseg = min(nseg_try, n_seg_total - s_cur);
+            if (tid < nseg) {
+                const int sidx = s_cur + tid;
+                const int grp = sidx / n_lights, l = sidx - grp * n_lights;
+                const Grp& G = s.grp[grp];
+                const short4 lt = p.lights[l];
+                // light bin, alternative.cpp:729-732 ('/' truncates toward zero)
+                const int lbx = lt.x / kBin, lby = (d.H - lt.y - lt.z) / kBin, lbz = lt.z / kBin;
+                const float dx = (float)lbx - (float)bx, dy = (float)lby - (float)ty, dz = (float)lbz - (float)G.gz;
+                const float big = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+                Seg& g = s.seg[tid];
+                g.steps = (int)big;  // 0 when big < 1 (then the NaN step is never used)
+                g.sx = dx / big;
+                g.sy = dy / big;
+                g.sz = dz / big;
+                g.light = l;
+                g.grp = grp;
+                g.start = flat_bin(d, bx, ty, G.gz);  // start bin of every pixel of the group (alternative.cpp:724-727)
+                g.ka = tid == 0 ? ka_cur : 0;
+                g.kb = (tid == 0 && kb_try >= 0) ? kb_try : g.steps;
+                g.count = 0;
+                g.fill = 0;
+                g.octant = group_octant(G, lt);
+            }
+            for (int t = tid; t < kHashSize; t += kT) s.r.hash[t] = kEmpty;
+            __syncthreads();
+            if (tid == 0) {
+                // run length: about one work item per thread, so the serial part of a walk stays short
+                int steps = 0;
+                for (int q = 0; q < nseg; q++) steps += s.seg[q].kb - s.seg[q].ka;
+                const int run = min(kMaxRun, max(1, (steps + kT - 1) / kT));
+                int items = 0;
+                for (int q = 0; q < nseg; q++) {
+                    s.seg[q].item0 = items;
+                    items += (s.seg[q].kb - s.seg[q].ka + run - 1) / run;
+                }
+                s.n_items = items;
+                s.run = run;
+                s.n_occ = 0;
+                s.overflow = 0;
+            }
+            __syncthreads();
+            mark(kPhSetup);
+
+            // C. walk.  One thread per run of kRun steps of one segment.  The run is processed in
+            // sub-chunks: first the distinct probed bins of up to 8 steps are listed (ALU only) in a
+            // thread-private column of shared scratch, then their 4-bit counts are fetched as one batch
+            // of independent loads.
+            const int n_items = s.n_items, kRun = s.run;
+            int* scratch = reinterpret_cast<int*>(s.r.list);  // [kScratchRows][kT]; the box list is idle now
+            for (int it = tid; it < n_items; it += kT) {
+                int q = 0;
+                while (q + 1 < nseg && s.seg[q + 1].item0 <= it) q++;
+                const Seg& g = s.seg[q];
+                const int k0 = g.ka + (it - g.item0) * kRun, k1 = min(k0 + kRun, g.kb);
+                const float sx = g.sx, sy = g.sy, sz = g.sz;
+                const int start = g.start;
+                // sequential fp32 accumulation from the start bin (quirk Q15)
+                float px = (float)bx, py = (float)ty, pz = (float)s.grp[g.grp].gz;
+                int k = 0;
+                for (; k + 8 <= k0; k += 8) {
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        px = px + sx;
+                        py = py + sy;
+                        pz = pz + sz;
+                    }
+                }
+                for (; k < k0; k++) {
+                    px = px + sx;
+                    py = py + sy;
+                    pz = pz + sz;
+                }
+                int x0 = (int)px, y0 = (int)py, z0 = (int)pz;
+                const int sxy = d.HH * d.HL;
+                while (k < k1) {
+                    int n = 0;
+                    for (int u = 0; u < 8 && k < k1 && n + 7 <= kScratchRows; u++, k++) {
+                        px = px + sx;
+                        py = py + sy;
+                        pz = pz + sz;
+                        const int x1 = (int)px, y1 = (int)py, z1 = (int)pz;
+                        // The 7 probes of a step are the bins {x0|x1} x {y0|y1} x {z0|z1} minus
+                        // "all old" (the all-old bin was the previous step's last probe, or the
+                        // start bin, which is skipped anyway: quirk Q16).  Distinct bins among
+                        // them = the non-empty subsets of the axes whose bin changed.
+                        const int changed = (x1 != x0) | (y1 != y0) << 1 | (z1 != z0) << 2;
+                        const int fx0 = x0 * sxy, fx1 = x1 * sxy, fy0 = y0 * d.HL, fy1 = y1 * d.HL;
+                        for (int sub = changed; sub; sub = (sub - 1) & changed) {
+                            const int f = ((sub & 1) ? fx1 : fx0) + ((sub & 2) ? fy1 : fy0) + ((sub & 4) ? z1 : z0);
+                            if (f == start || (unsigned)f >= (unsigned)d.V) continue;  // Q16 / Q18
+                            scratch[n * kT + tid] = f;
+                            n++;
+                        }
+                        x0 = x1;
+                        y0 = y1;
+                        z0 = z1;
+                    }
+                    // the 4-bit counts of the sub-chunk, in batches of 8 independent loads; occupied bins
+                    // go straight to the shared list
+                    int boxes = 0;
+                    for (int i0 = 0; i0 < n; i0 += 8) {
+                        int f[8], c[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            f[u] = i0 + u < n ? scratch[(i0 + u) * kT + tid] : -1;
+                            c[u] = f[u] >= 0 ? (__ldg(&p.occ4[f[u] >> 3]) >> ((f[u] & 7) * 4)) & 7 : 0;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 8; u++)
+                            if (c[u]) {
+                                const int o = atomicAdd(&s.n_occ, 1);
+                                if (o < kOccCap) {
+                                    s.r.occ_bin[o] = (unsigned)f[u];
+                                    s.r.occ_meta[o] = (unsigned char)(q << 3 | c[u]);
+                                }
+                                boxes += c[u];
+                            }
+                    }
+                    if (boxes) atomicAdd(&s.seg[q].count, boxes);
+                }
+            }
+            __syncthreads();
+            mark(kPhWalk);
+            const int n_occ = s.n_occ;  // every occupied bin holds >= 1 box, so n_occ <= sum of counts
+            // D. how many leading segments go into this round?  (every thread, redundantly)
+            // The de-duplication set must stay sparse (candidates <= 3/4 of its slots) and the
+            // occupied-bin list must be complete.  The box list itself is shared out evenly: after
+            // de-duplication and the shaft cull a segment keeps a small fraction of its candidates,
+            // so each of the n_fit segments gets room for min(candidates, kListCap / n_fit) boxes;
+            // if one needs more, the round is redone with half the segments.
+            int n_fit = 0;
+            {
+                int total = 0;
+                while (n_fit < nseg && total + s.seg[n_fit].count <= kHashSize * 3 / 4) {
+                    total += s.seg[n_fit].count;
+                    n_fit++;
+                }
+            }
+            if (n_fit == 0 || n_occ > kOccCap) {  // shrink: fewer segments first, then fewer steps of the first one
+                if (nseg > 1) {
+                    nseg_try = max(1, nseg / 2);
+                } else {
+                    const int ka = s.seg[0].ka, kb = s.seg[0].kb;
+                    kb_try = ka + max(1, (kb - ka) / 2);
+                }
+                continue;
+            }
+            const int share = kListCap / n_fit;
+            if (tid < n_fit) {  // base of segment tid in the box list (read after the next barrier)
+                int base = 0;
+                for (int q = 0; q < tid; q++) base += min(s.seg[q].count, share);
+                s.seg[tid].base = base;
+            }
+
+            // E. gather: one lane per candidate slot.  Each warp takes 32 occupied bins, scans their
+            // counts and expands them into (bin, slot) pairs with shuffles, so that the dependent
+            // loads (entity id -> box) run with dense lanes: entity -> de-duplicate -> box ->
+            // shaft cull -> the segment's part of the box list.
+            const bool cull_on = !(p.debug_flags & 1);
+            for (int ob = tid - lane; ob < n_occ; ob += kT) {
+                const bool have = ob + lane < n_occ;
+                const unsigned my_bin = have ? s.r.occ_bin[ob + lane] : 0u;
+                const unsigned my_meta = have ? s.r.occ_meta[ob + lane] : 0u;
+                const int my_c = (have && (int)(my_meta >> 3) < n_fit) ? (int)(my_meta & 7u) : 0;
+                int incl = my_c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int total = __shfl_sync(0xffffffffu, incl, 31);
+                for (int t0 = 0; t0 < total; t0 += 32) {
+                    const int t = t0 + lane;
+                    int src = 0;  // first lane whose inclusive prefix exceeds t
+#pragma unroll
+                    for (int step = 16; step; step >>= 1) {
+                        const int v = __shfl_sync(0xffffffffu, incl, src + step - 1);
+                        if (v <= t) src += step;
+                    }
+                    src = min(src, 31);
+                    const unsigned bin = __shfl_sync(0xffffffffu, my_bin, src);
+                    const unsigned meta = __shfl_sync(0xffffffffu, my_meta, src);
+                    const int cnt_src = __shfl_sync(0xffffffffu, my_c, src);
+                    const int slot_i = t - (__shfl_sync(0xffffffffu, incl, src) - cnt_src);
+                    if (t >= total) continue;
+                    const int q = meta >> 3;
+                    const int ent = __ldg(&p.ids[(size_t)bin * kSlots + slot_i]);
+                    const unsigned key = (unsigned)q << 26 | (unsigned)ent;
+                    unsigned h = (key * 2654435761u) >> (32 - kHashBits);
+                    bool fresh_key;
+                    for (;;) {
+                        const unsigned old = atomicCAS(&s.r.hash[h], kEmpty, key);
+                        if (old == kEmpty || old == key) {
+                            fresh_key = old == kEmpty;
+                            break;
+                        }
+                        h = (h + 1) & (kHashSize - 1);
+                    }
+                    if (!fresh_key) continue;
+                    const Box b = unpack_box(__ldg(&p.boxes[ent]));
+                    const Seg& sg = s.seg[q];
+                    const Grp& G = s.grp[sg.grp];
+                    // Shaft cull against the bounds of the group's ray origins.  The origin is cast to short in
+                    // the reference (alternative.cpp:720-722): only cull when nothing can wrap.
+                    bool can_cull = cull_on;
+                    float org_lo[3], org_hi[3];
+#pragma unroll
+                    for (int a = 0; a < 3; a++) {
+                        org_lo[a] = (float)G.omin[a];
+                        org_hi[a] = (float)G.omax[a];
+                        can_cull = can_cull && G.omin[a] >= -32768 && G.omax[a] <= 32767;
+                    }
+                    if (can_cull) {
+                        const short4 lt = p.lights[sg.light];
+                        const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
+                        const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
+                        const float lp[3] = {(float)lt.x, (float)lt.y, (float)lt.z};
+                        if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
+                    }
+                    int base = 0;
+                    for (int r = 0; r < q; r++) base += min(s.seg[r].count, share);
+                    const int nth = atomicAdd(&s.seg[q].fill, 1);
+                    if (nth >= min(sg.count, share)) {
+                        s.overflow = 1;
+                        continue;
+                    }
+                    store_box(s.r.list, base + nth, b, ent, sg.octant);
+                }
+            }
+            __syncthreads();
+            mark(kPhGather);
+            if (s.overflow) {  // some segment kept more than its share: fewer segments, then fewer steps
+                if (n_fit > 1) {
+                    nseg_try = max(1, n_fit / 2);
+                } else {
+                    const int ka = s.seg[0].ka, kb = s.seg[0].kb;
+                    kb_try = ka + max(1, (kb - ka) / 2);
+                    nseg_try = 1;
+                }
+                continue;
+            }
+            if (p.phase_cycles && tid == 0) {  // debug: candidate boxes found / kept after de-dup + cull
+                unsigned long long found = 0, kept = 0;
+                for (int q = 0; q < n_fit; q++) {
+                    found += s.seg[q].count;
+                    kept += s.seg[q].fill;
+                }
+                atomicAdd(&p.phase_cycles[10], found);
+                atomicAdd(&p.phase_cycles[11], kept);
+                atomicAdd(&p.phase_cycles[12], 1ull);
+            }
+
+            // F. shade: one lane per pixel of the groups this round touches
+            const int grp_first = s.seg[0].grp, grp_last = s.seg[n_fit - 1].grp;
+            const int pix0 = s.grp[grp_first].p0, pix1 = s.grp[grp_last].p0 + s.grp[grp_last].n;
+            const bool last_seg_done = s.seg[n_fit - 1].kb == s.seg[n_fit - 1].steps;
+            for (int qb = tid - lane; qb < pix1 - pix0; qb += kT) {
+                const int qi = pix0 + qb + lane;
+                const bool valid = qi < pix1;
+                const int pidx = valid ? s.pix[qi] : 0;
+                const int row = pidx / kBin;
+                const int j = ty * kBin + row, ipx = bx * kBin + (pidx - row * kBin);
+                const int g_z = s.z[pidx], g_ent = s.ent[pidx];
+                const unsigned g_w = s.w[pidx];
+                const int g_y = (short)(d.H - j) - g_z;  // quirk Q11
+                // the pixel's segments in this round: [qa, qe)
+                const int grp = valid ? group_index(g_z / kBin) : grp_first;
+                const int qa = max(0, grp * n_lights - s_cur), qe = min(n_fit, (grp + 1) * n_lights - s_cur);
+                const bool fresh = grp * n_lights >= s_cur && s.seg[qa].ka == 0;        // light 0 starts here
+                const bool final_round = (grp + 1) * n_lights - s_cur <= n_fit && (grp != grp_last || last_seg_done);
+                // raster row, or the row's slot in the stripe-major staging frame (rank-contiguous)
+                const int jo = p.out_stripe_T ? ((ty % d.stripe_n) * p.out_stripe_T + ty / d.stripe_n) * kBin + row : j;
+                const size_t at = (size_t)jo * d.W + ipx;
+                float4 tex = make_float4(0.f, 0.f, 0.f, 0.f);
+                float acc = 0.f;
+                bool shadowed = false;
+                if (valid) {
+                    tex = __ldg(&p.texel_tab[g_w]);  // normal + palette colour of the hit texel
+                    if (!fresh) {  // state parked by the previous round (sign bit: shadowed so far by a split light)
+                        const unsigned park = reinterpret_cast<const unsigned*>(p.out)[at];
+                        acc = __uint_as_float(park & 0x7fffffffu);
+                        shadowed = park >> 31;
+                    }
+                }
+                // Ray origin, alternative.cpp:720-722
+                const float ox = (float)(short)ipx, oy = (float)(short)g_y, oz = (float)(short)g_z;
+                const int wqa = __reduce_min_sync(0xffffffffu, valid ? qa : n_fit);
+                const int wqe = __reduce_max_sync(0xffffffffu, valid ? qe : 0);
+                for (int q = wqa; q < wqe; q++) {
+                    const Seg& sg = s.seg[q];
+                    const bool mine = valid && q >= qa && q < qe;
+                    const short4 lt = p.lights[sg.light];
+                    if (sg.ka == 0 && mine) shadowed = false;
+                    // towards_light, L1-normalised (alternative.cpp:711-715, sprites.hpp:28-35)
+                    float tx = (float)(lt.x - ipx), tyv = (float)(lt.y - g_y), tz = (float)(lt.z - g_z);
+                    const float len = fabsf(tx) + fabsf(tyv) + fabsf(tz);
+                    tx = tx / len;
+                    tyv = tyv / len;
+                    tz = tz / len;
+                    // alternative.cpp:745-747; a term of 0 adds +0 whether visible or not (Q19)
+                    const float lam = std_max(0.f, tex.x * tx + tex.y * tyv + tex.z * tz);
+                    if (p.dbg_t && mine && sg.light == p.dbg_light && sg.ka == 0)
+                        p.dbg_t[(size_t)j * d.W + ipx] = make_float4(tx, tyv, tz, lam);
+                    const bool lit_candidate = mine && lam > 0.f;
+                    const int n = sg.fill;
+                    const bool test = lit_candidate && !shadowed && n > 0;
+                    // direction_inverse, alternative.cpp:717-719 (only needed when testing)
+                    float ix = 0.f, iy = 0.f, iz = 0.f;
+                    if (test) {
+                        ix = 1.f / tx;
+                        iy = 1.f / tyv;
+                        iz = 1.f / tz;
+                    }
+                    // a NaN can only arise from a zero (or NaN) direction component (quirk Q13)
+                    const bool nan_free = fabsf(tx) > 0.f && fabsf(tyv) > 0.f && fabsf(tz) > 0.f;
+                    const float4* boxes = s.r.list + 2 * sg.base;
+                    if (__any_sync(0xffffffffu, test)) {
+                        // warp-uniform choice of the slab-test variant
+                        bool hit = false;
+                        if (sg.octant >= 0) {
+                            if (test) hit = any_box_hit<0>(boxes, n, g_ent, ox, oy, oz, ix, iy, iz);
+                        } else if (!__any_sync(0xffffffffu, test && !nan_free)) {
+                            if (test) hit = any_box_hit<1>(boxes, n, g_ent, ox, oy, oz, ix, iy, iz);
+                        } else {
+                            if (test) hit = any_box_hit<2>(boxes, n, g_ent, ox, oy, oz, ix, iy, iz);
+                        }
+                        if (hit) shadowed = true;
+                    }
+                    if (sg.kb == sg.steps && lit_candidate && !shadowed) acc = acc + lam;
+                }
+                if (valid && qa < qe) {
+                    if (final_round) {
+                        if (p.dbg_factor) p.dbg_factor[(size_t)j * d.W + ipx] = acc + p.ambient;
+                        // alternative.cpp:735 / 757-758
+                        s.w[pidx] = quantise(__float_as_uint(tex.w), std_min(1.f, acc + p.ambient));
+                    } else {
+                        reinterpret_cast<unsigned*>(p.out)[at] = __float_as_uint(acc) | (shadowed ? 0x80000000u : 0u);
+                    }
+                }
+            }
+            mark(kPhShade);
+
+            // advance past the processed segments
+            if (last_seg_done) {
+                s_cur += n_fit;
+                ka_cur = 0;
+            } else {  // a split light: n_fit == 1
+                s_cur += n_fit - 1;
+                ka_cur = s.seg[n_fit - 1].kb;
+            }
+            kb_try = -1;
+            nseg_try = kSegMax;
+        }
+        g_done = gmin + (kGroupMax - 1);
+    }
+
+    // ---- 16-byte stores of the finished tile rows ----
+    __syncthreads();
+    if (!p.gbuf_only) {
+        for (int v = tid; v < kPix / 4; v += kT) {
+            const int row = v / (kBin / 4), j = ty * kBin + row;
+            if (j < ra || j >= rb) continue;
+            const uint4 px = *reinterpret_cast<const uint4*>(&s.w[4 * v]);
+            const int jo = p.out_stripe_T ? ((ty % d.stripe_n) * p.out_stripe_T + ty / d.stripe_n) * kBin + row : j;
+            const size_t at = (size_t)jo * d.W + bx * kBin + 4 * (v % (kBin / 4));
+            *reinterpret_cast<uint4*>(&p.out[at]) = px;
+            // Fused exchange: the same chunk goes straight into every peer GPU's frame (posted writes over
+            // NVLink), so no all-gather pass over the frame is needed afterwards.
+            for (int r = 0; r < p.n_peer_out; r++) *reinterpret_cast<uint4*>(&p.peer_out[r][at]) = px;
+        }
+    }
+    mark(kPhTail);
+    if (p.tile_cost && tid == 0) {
+        const long long dt = clock64() - t_begin;
+        p.tile_cost[ty * d.HW + bx] = (unsigned)min(dt, (long long)0xffffffffu);
+    }
+}
+
+size_t tile_smem_bytes() { return sizeof(TileSmem); }
+
+cudaError_t configure_tile() {
+    return cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+}
+
+cudaError_t launch_tile(const TileParams& p, cudaStream_t st) {
+    int first, tile_rows;
+    owned_tile_rows(p.d, first, tile_rows);
+    if (tile_rows <= 0) return cudaSuccess;
+    k_tile<<<tile_rows * p.d.HW, kT, sizeof(TileSmem), st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- tile order: longest tiles first ---------------------------------------------------------------
+// The cost of a tile (shadow-walk lengths, occluder counts) varies by more than an order of
+// magnitude over a many-light frame, and the hardware hands CTAs to SMs in launch order: with the
+// raster order a few expensive tiles that happen to start late leave most SMs idle at the end of the
+// kernel.  Every CTA records its cycle count; before the next frame the owned tiles are
+// counting-sorted by the previous frame's cost, most expensive first (LPT scheduling).  The order
+// only permutes which CTA renders which tile, never what is rendered.
+__global__ void __launch_bounds__(1024)
+k_tile_order(const unsigned* __restrict__ cost, int* __restrict__ order, ViewDims d, int tile_row_first, int tile_rows) {
+    constexpr int kBuckets = 256;
+    __shared__ unsigned s_max;
+    __shared__ int s_hist[kBuckets], s_base[kBuckets];
+    const int n = tile_rows * d.HW, tid = threadIdx.x;
+    const int stripe = max(d.stripe_n, 1);
+    if (tid == 0) s_max = 1u;
+    if (tid < kBuckets) s_hist[tid] = 0;
+    __syncthreads();
+    unsigned mx = 0u;
+    for (int t = tid; t < n; t += blockDim.x) mx = max(mx, cost[(tile_row_first + (t / d.HW) * stripe) * d.HW + t % d.HW]);
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((tid & 31) == 0) atomicMax(&s_max, mx);
+    __syncthreads();
+    const float scale = (float)(kBuckets - 1) / (float)s_max;
+    auto bucket = [&](int t) {  // bucket 0 = most expensive
+        const unsigned c = cost[(tile_row_first + (t / d.HW) * stripe) * d.HW + t % d.HW];
+        return (kBuckets - 1) - min(kBuckets - 1, (int)((float)c * scale));
+    };
+    for (int t = tid; t < n; t += blockDim.x) atomicAdd(&s_hist[bucket(t)], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int b = 0; b < kBuckets; b++) {
+            s_base[b] = run;
+            run += s_hist[b];
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < n; t += blockDim.x) order[atomicAdd(&s_base[bucket(t)], 1)] = t;
+}
+
+cudaError_t launch_tile_order(const unsigned* cost, int* order, const ViewDims& d, cudaStream_t st) {
+    int first, tile_rows;
+    owned_tile_rows(d, first, tile_rows);
+    if (tile_rows <= 0) return cudaSuccess;
+    k_tile_order<<<1, 1024, 0, st>>>(cost, order, d, first, tile_rows);
+    return cudaGetLastError();
+}
+
+}  // namespace par

@@ -41,7 +41,9 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_peer_export", "par_peer_import", "par_peer_set", "par_render_device_peers", "par_read_frame",
            "par_read_stripes", "par_register_host", "par_unregister_host", "par_submit_frame", "par_wait_frame",
            "par_get_gbuffer", "par_get_grid", "par_get_stats", "par_grid_volume",
-           "par_debug_phase_timing",
+           "par_debug_phase_timing", "par_debug_intermediates", "par_set_atlas_sized", "par_update_entities",
+           "par_submit_update", "par_set_output_pitch", "par_read_frame_pitched", "par_render_resident",
+           "par_exchange_setup",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
            "par_light_default", "par_scene_synthetic", "par_apply_key", "par_draw_overlay",
            "par_draw_overlay_at", "par_set_cursor", "par_cursor_pixel"]
@@ -51,18 +53,18 @@ class Config(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("length", C.c_int32),
                 ("device", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
                 ("ambient", C.c_float), ("stripe_count", C.c_int32), ("stripe_index", C.c_int32),
-                ("reserved", C.c_int32 * 3)]
+                ("tile_order", C.c_int32), ("reserved", C.c_int32 * 2)]
 
 
 class Stats(C.Structure):
-    _fields_ = [("ms_grid_build", C.c_float), ("ms_primary", C.c_float), ("ms_shade", C.c_float),
+    _fields_ = [("ms_grid_build", C.c_float), ("ms_render", C.c_float), ("ms_reserved", C.c_float),
                 ("ms_total", C.c_float), ("kernel_launches", C.c_int32),
                 ("n_entities", C.c_int32), ("n_survivors", C.c_int32), ("n_inserts", C.c_int32),
-                ("rays", C.c_uint64), ("slab_tests", C.c_uint64), ("ms_walks", C.c_float),
+                ("rays", C.c_uint64), ("slab_tests", C.c_uint64), ("ms_reserved2", C.c_float),
                 ("ms_readback", C.c_float), ("reserved", C.c_int32 * 2)]
 
     def as_dict(self):
-        return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
+        return {k: getattr(self, k) for k, _ in self._fields_ if "reserved" not in k}
 
 
 class ParError(RuntimeError):
@@ -132,6 +134,14 @@ def lib():
         L.par_get_stats.argtypes = [vp, C.POINTER(Stats)]
         L.par_grid_volume.argtypes = [vp]
         L.par_debug_phase_timing.argtypes = [vp, i32, vp]
+        L.par_debug_intermediates.argtypes = [vp, vp, i32, i32, vp, vp]
+        L.par_set_atlas_sized.argtypes = [vp, i32, vp, vp, vp, vp, vp, vp, i32]
+        L.par_update_entities.argtypes = [vp, i32, i32, vp, vp]
+        L.par_submit_update.argtypes = [vp, i32, i32, vp, vp, vp, i32, vp]
+        L.par_set_output_pitch.argtypes = [vp, C.c_size_t]
+        L.par_read_frame_pitched.argtypes = [vp, vp, C.c_size_t]
+        L.par_render_resident.argtypes = [vp, vp, i32]
+        L.par_exchange_setup.argtypes = [vp, i32]
         L.par_sprite_tile_floor.argtypes = [vp]
         L.par_sprite_tile_floor.restype = None
         L.par_palette_default.argtypes = [vp]
@@ -256,10 +266,10 @@ class Renderer:
     """
 
     def __init__(self, W, H, L, device=0, row_begin=0, row_end=0, ambient=0.0, stripe_count=0,
-                 stripe_index=0):
+                 stripe_index=0, tile_order=0):
         self.W, self.H, self.L = W, H, L
         self._h = C.c_void_p()
-        cfg = Config(W, H, L, device, row_begin, row_end, ambient, stripe_count, stripe_index)
+        cfg = Config(W, H, L, device, row_begin, row_end, ambient, stripe_count, stripe_index, tile_order)
         self.row_begin = row_begin
         self.row_end = row_end if (row_begin or row_end) else H
         _check(lib().par_create(C.byref(self._h), C.byref(cfg)))
@@ -287,16 +297,71 @@ class Renderer:
     def sync(self):
         _check(lib().par_sync(self._h))
 
+    def stream(self) -> int:
+        """cudaStream_t (as an integer) all work of the context is ordered on."""
+        return lib().par_get_stream(self._h)
+
     def set_atlas(self, sprites=None, palette=None):
         sprites = tile_floor() if sprites is None else np.ascontiguousarray(sprites, SPRITE)
         palette = default_palette() if palette is None else np.ascontiguousarray(palette, COLOR)
         _check(lib().par_set_atlas(self._h, _p(sprites), len(sprites), _p(palette), len(palette)))
+
+    def set_atlas_sized(self, widths, heights, color, depth, normal, palette=None):
+        """par_set_atlas_sized: sprites of their own width x height (tables concatenated, row-major)."""
+        widths = np.ascontiguousarray(widths, np.int32)
+        heights = np.ascontiguousarray(heights, np.int32)
+        color = np.ascontiguousarray(color, np.int32)
+        depth = np.ascontiguousarray(depth, np.int32)
+        normal = np.ascontiguousarray(normal, np.float32)
+        palette = default_palette() if palette is None else np.ascontiguousarray(palette, COLOR)
+        _check(lib().par_set_atlas_sized(self._h, len(widths), _p(widths), _p(heights), _p(color), _p(depth),
+                                         _p(normal), _p(palette), len(palette)))
 
     def set_scene(self, aabbs, sprite_ids=None):
         aabbs = np.ascontiguousarray(aabbs, AABB)
         if sprite_ids is not None:
             sprite_ids = np.ascontiguousarray(sprite_ids, np.int32)
         _check(lib().par_set_scene(self._h, _p(aabbs), _p(sprite_ids), len(aabbs)))
+
+    def update_entities(self, first, aabbs, sprite_ids=None):
+        """par_update_entities: entities [first, first + len(aabbs)) of the resident scene get new boxes."""
+        aabbs = np.ascontiguousarray(aabbs, AABB)
+        if sprite_ids is not None:
+            sprite_ids = np.ascontiguousarray(sprite_ids, np.int32)
+        _check(lib().par_update_entities(self._h, first, len(aabbs), _p(aabbs), _p(sprite_ids)))
+
+    def submit_update(self, first, aabbs, lights, out, sprite_ids=None):
+        """par_submit_update: pipelined frame from the resident scene with entities [first, ...) replaced."""
+        aabbs = np.ascontiguousarray(aabbs, AABB)
+        lights = np.ascontiguousarray(lights, LIGHT)
+        if sprite_ids is not None:
+            sprite_ids = np.ascontiguousarray(sprite_ids, np.int32)
+        _check(lib().par_submit_update(self._h, first, len(aabbs), _p(aabbs), _p(sprite_ids), _p(lights),
+                                       len(lights), _p(out)))
+
+    def render_resident(self, lights):
+        """par_render_resident: loader + render kernel (+ multi-GPU exchange) from the resident scene, async."""
+        lights = np.ascontiguousarray(lights, LIGHT)
+        _check(lib().par_render_resident(self._h, _p(lights), len(lights)))
+
+    def exchange_setup(self, root=-1):
+        _check(lib().par_exchange_setup(self._h, root))
+
+    def set_output_pitch(self, pitch_bytes):
+        _check(lib().par_set_output_pitch(self._h, pitch_bytes))
+
+    def read_frame_pitched(self, out, pitch_bytes):
+        """D2H of the whole frame into `out` (any array of >= H * pitch bytes), rows pitch_bytes apart; async."""
+        _check(lib().par_read_frame_pitched(self._h, _p(out), pitch_bytes))
+        return out
+
+    def intermediates(self, lights, light):
+        """par_debug_intermediates: (t_lam (H,W,4) float32, factor (H,W) float32) of the latest frame."""
+        lights = np.ascontiguousarray(lights, LIGHT)
+        t = np.zeros((self.H, self.W, 4), np.float32)
+        f = np.zeros((self.H, self.W), np.float32)
+        _check(lib().par_debug_intermediates(self._h, _p(lights), len(lights), light, _p(t), _p(f)))
+        return t, f
 
     def rebuild_grid(self):
         _check(lib().par_rebuild_grid(self._h))
@@ -397,14 +462,14 @@ class Renderer:
         _check(lib().par_get_grid(self._h, _p(count), _p(ids)))
         return count, ids.reshape(V, 8)
 
-    PHASES = ["load", "find", "compact", "setup", "walk", "counts", "decide", "gather", "shade", "tail"]
+    PHASES = ["primary", "group", "setup", "walk", "gather", "shade", "tail", "p7", "p8", "p9"]
 
     def phase_timing(self, enable=True):
         """Debug: per-phase cycle totals of k_shade since the last call (dict), then (re)arm."""
         out = np.zeros(16, np.uint64)
         _check(lib().par_debug_phase_timing(self._h, int(enable), _p(out)))
         d = {n: int(out[i]) for i, n in enumerate(self.PHASES)}
-        d.update(boxes_found=int(out[10]), boxes_kept=int(out[11]), pixel_lights=int(out[12]))
+        d.update(boxes_found=int(out[10]), boxes_kept=int(out[11]), rounds=int(out[12]))
         return d
 
     def stats(self):

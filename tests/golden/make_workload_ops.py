@@ -37,10 +37,12 @@ def main():
         W, H, L, make = wl[name]
         boxes, lights = make()
         t = time.time()
-        r = O.render(W, H, L, boxes, lights, want_texel=False)
+        r = O.render(W, H, L, boxes, lights, want_texel=True)
         res[name] = {"view": [W, H, L], "n_entities": int(len(boxes)), "n_lights": int(len(lights)),
                      "rays": W * H * (1 + len(lights)), "counters": r["counters"],
                      "algorithmic_ops": r["ops"], "frame_fnv1a64": "%016x" % O.fnv1a64(r["rgba"]),
+                     "gbuf_fnv1a64": "%016x" % O.fnv1a64(r["gbuf"]),      # raw Pixel[] bytes (28 B each)
+                     "texel_fnv1a64": "%016x" % O.fnv1a64(r["texel"]),    # int32 texel-index plane, -1 = miss
                      "oracle_seconds_container": round(time.time() - t, 2)}
         print(name, res[name]["algorithmic_ops"], res[name]["oracle_seconds_container"], flush=True)
         json.dump(res, open(OUT, "w"), indent=1, sort_keys=True)

@@ -1,7 +1,7 @@
-// Property test of the three slab-test variants of k_shade (pixel-art-raytracer_b200/csrc/shade.cu)
+// Property test of the three slab-test variants of k_tile (pixel-art-raytracer_b200/csrc/tile.cu)
 // on the CPU.  TEST INFRASTRUCTURE: built and run by tests/test_slab_variants_property.py, which
 // extracts std_min/std_max (par_device.cuh) and slab_hit_exact / slab_hit_fast / slab_hit_near_far
-// (shade.cu) verbatim into slab_host.h.
+// (tile.cu) verbatim into slab_host.h.
 //
 // Claims under test, against the oracle's predicate (orc_slab_hit_point: ray set-up of
 // alternative.cpp:712-722 + AABB::intersect 40-83):
@@ -74,7 +74,7 @@ int main(int argc, char** argv) {
         const int want = orc_slab_hit_point(&b, o[0], o[1], o[2], &lt);
         hits += want;
 
-        // the product's ray set-up (shade.cu, phase F): same operations as the reference
+        // the product's ray set-up (tile.cu, phase F): same operations as the reference
         float tx = (float)(L[0] - o[0]), ty = (float)(L[1] - o[1]), tz = (float)(L[2] - o[2]);
         const float len = fabsf(tx) + fabsf(ty) + fabsf(tz);
         tx = tx / len;

@@ -623,3 +623,465 @@ def test_error_paths(par):
         with pytest.raises(par.ParError):
             r.set_scene(par.scene_default()[:10], sprite_ids=np.full(10, 3, np.int32))
             r.render(par.light_default())
+
+
+# ------------------------------------------------------------------ round 2: full-size configs, A/B, intermediates
+
+def _workload(par, name):
+    if name in ("c1", "c2", "c4"):
+        return par.scene_default(), par.light_default()
+    W, H, L = {"c3": (3840, 2160, 2160), "c5": (7680, 4320, 4320), "c5b": (7680, 4320, 4320)}[name]
+    return par.scene_synthetic(W, H, L, n=40000 if name == "c5b" else 10000, n_lights=16)
+
+
+@pytest.fixture(scope="session")
+def workload_ops():
+    import json
+    import os
+    from conftest import ROOT
+    with open(os.path.join(ROOT, "tests", "golden", "workload_ops.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c5", "c5b"])
+def test_full_size_configs_vs_oracle_hashes(par, oracle, workload_ops, name):
+    """Every BASELINE config at FULL size: the whole frame, the raw Pixel[] G-buffer and the texel-index
+    plane hash (FNV-1a-64) to what the oracle rendered for the same recipe
+    (tests/golden/make_workload_ops.py; c5 / c5b take minutes on the CPU, hence committed hashes)."""
+    g = workload_ops[name]
+    W, H, L = g["view"]
+    boxes, lights = _workload(par, name)
+    assert len(boxes) == g["n_entities"] and len(lights) == g["n_lights"]
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        rgba, gbuf, _ = r.render(lights, want_gbuf=True)
+        assert "%016x" % oracle.fnv1a64(rgba) == g["frame_fnv1a64"], "frame"
+        assert "%016x" % oracle.fnv1a64(gbuf) == g["gbuf_fnv1a64"], "G-buffer bytes"
+        del gbuf
+        _, texel = r.gbuffer()
+        assert "%016x" % oracle.fnv1a64(texel) == g["texel_fnv1a64"], "texel indices"
+        # the production frame (no G-buffer written, longest-first tile order from the previous frame's
+        # costs, graph replay) is the same frame
+        for _ in range(3):
+            r.render_resident(lights)
+        got = r.read_frame()
+        r.sync()
+        assert np.array_equal(_u32(got), _u32(rgba))
+
+
+@pytest.mark.parametrize("name", ["c3", "c2"])
+def test_shaft_cull_off_gives_identical_bytes(par, monkeypatch, name):
+    """The shaft cull only drops boxes no ray of the group can hit: switching it off
+    (PAR_DEBUG_FLAGS=1) must not change a byte of a full-size frame."""
+    W, H, L = 3840, 2160, 2160
+    boxes, lights = _workload(par, name)
+    frames = []
+    for flags in ("0", "1"):
+        monkeypatch.setenv("PAR_DEBUG_FLAGS", flags)
+        with par.Renderer(W, H, L) as r:
+            r.set_atlas()
+            r.set_scene(boxes)
+            frames.append(r.render(lights)[0])
+    assert np.array_equal(_u32(frames[0]), _u32(frames[1]))
+
+
+def _ulp_diff(a, b):
+    """Distance in units in the last place between float32 arrays (NaN == NaN, +0 == -0)."""
+    ia = a.view(np.int32).astype(np.int64)
+    ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7fffffff), ia)
+    ib = np.where(ib < 0, -(ib & 0x7fffffff), ib)
+    d = np.abs(ia - ib)
+    both_nan = np.isnan(a) & np.isnan(b)
+    return np.where(both_nan, 0, d)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_fp32_intermediates_within_one_ulp(par, oracle, seed):
+    """SURVEY.md §8(d) tolerance: the fp32 intermediates — the L1-normalised light direction t, the
+    Lambert term and acc + ambient — within 1 ULP of the oracle's for every hit pixel and light
+    (stated allowance 1 ULP; the design target, IEEE arithmetic without contraction, is 0 and the
+    measured maximum is asserted to be 0 too), with RGBA exact."""
+    rng = np.random.default_rng(4200 + seed)
+    W, H, L = [(480, 320, 320), (640, 480, 480), (320, 640, 640)][seed]
+    atlas, pal = _random_atlas(rng, 3, 5)
+    boxes, lights, ids = _random_scene(rng, W, H, L, 2500, 5, n_sprites=3)
+    tol_ulp = 1
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas(atlas, pal)
+        r.set_scene(boxes, ids)
+        rgba, gbuf, _ = r.render(lights, want_gbuf=True)
+        _, texel = r.gbuffer()
+        hit = texel >= 0
+        assert hit.any() and (~hit).any()
+        worst = 0
+        for l in range(len(lights)):
+            ref = oracle.render(W, H, L, np.ascontiguousarray(boxes, oracle.AABB), np.ascontiguousarray(lights, oracle.LIGHT),
+                                atlas=np.ascontiguousarray(atlas, oracle.SPRITE), palette=np.ascontiguousarray(pal, oracle.COLOR),
+                                sprite_ids=ids, dbg_light=l)
+            t, f = r.intermediates(lights, l)
+            if l == 0:
+                assert np.array_equal(_u32(rgba), _u32(ref["rgba"]))
+            dt = _ulp_diff(t[hit], ref["t"][hit])
+            df = _ulp_diff(f[hit], ref["factor"][hit])
+            worst = max(worst, int(dt.max()), int(df.max()))
+            assert dt.max() <= tol_ulp and df.max() <= tol_ulp, f"light {l}: t {dt.max()} ulp, factor {df.max()} ulp"
+            assert not t[~hit].any() and not f[~hit].any()  # never evaluated for miss pixels (quirk Q19)
+        assert worst == 0, f"fp32 intermediates differ by up to {worst} ulp (allowed {tol_ulp}, expected 0)"
+
+
+# ------------------------------------------------------------------ round 2: sprites of their own size (Q7 lifted)
+
+def _sized_sprites(rng, dims, n_palette):
+    out = []
+    for (w, h) in dims:
+        out.append((rng.integers(0, n_palette, (h, w)), rng.integers(0, 24, (h, w)),
+                    rng.standard_normal((h, w, 3)).astype(np.float32)))
+    return out
+
+
+def _sized_scene(rng, W, H, L, n, dims, n_lights):
+    from par_b200 import AABB, LIGHT
+    a = np.zeros(n, AABB)
+    ids = rng.integers(0, len(dims), n).astype(np.int32)
+    wd = np.array([d[0] for d in dims])[ids]
+    hd = np.array([d[1] for d in dims])[ids]
+    a["px"] = rng.integers(-30, W + 30, n)
+    a["py"] = rng.integers(-30, 160, n)
+    a["pz"] = rng.integers(-60, L + 60, n)
+    a["ex"] = rng.integers(1, wd + 1)
+    a["ey"] = rng.integers(0, hd + 1)
+    a["ez"] = hd - a["ey"] - rng.integers(0, np.maximum(hd - a["ey"], 0) + 1)
+    l = np.zeros(n_lights, LIGHT)
+    l["x"] = rng.integers(-100, W + 200, n_lights)
+    l["y"] = rng.integers(-50, 400, n_lights)
+    l["z"] = rng.integers(-100, L + 100, n_lights)
+    return a, l, ids
+
+
+@pytest.mark.parametrize("dims", [[(16, 32)], [(32, 48)], [(16, 32), (32, 48), (20, 40), (7, 90), (64, 5)]])
+def test_sized_sprites(par, oracle, dims):
+    """Sprites of their own width x height (par_set_atlas_sized; the reference hard-codes 20 x 40,
+    alternative.cpp:328-332): texel = row * width + column, boxes up to the sprite's size."""
+    rng = np.random.default_rng(sum(w * 131 + h for w, h in dims))
+    W, H, L = 640, 480, 480
+    sprites = _sized_sprites(rng, dims, 6)
+    pal = _random_atlas(rng, 1, 6)[1]
+    boxes, lights, ids = _sized_scene(rng, W, H, L, 1800, dims, 4)
+    sized = oracle.ragged_atlas(sprites)
+    ref = oracle.render(W, H, L, np.ascontiguousarray(boxes, oracle.AABB), np.ascontiguousarray(lights, oracle.LIGHT),
+                        palette=np.ascontiguousarray(pal, oracle.COLOR), sprite_ids=ids, sized_atlas=sized)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas_sized(*sized, palette=pal)
+        r.set_scene(boxes, ids)
+        rgba, gbuf, stats = r.render(lights, want_gbuf=True)
+        _, texel = r.gbuffer()
+    assert (ref["texel"] >= 0).mean() > 0.2
+    _assert_frame_equal((rgba, gbuf, texel, stats), ref)
+
+
+def test_sized_sprite_padding_invariance(par, oracle):
+    """The 20x40 sprite embedded in a 32x48 one (extra columns / rows are never indexed by boxes of
+    extent <= 20 / 40) renders the default scene to the REAL reference's frame: pins the width
+    generalisation of the texel index to the reference."""
+    from conftest import sha256
+    base = par.tile_floor()[0]
+    color = np.full((48, 32), 3, np.int32)
+    depth = np.full((48, 32), 7, np.int32)
+    normal = np.ones((48, 32, 3), np.float32)
+    color[:40, :20] = base["color"].reshape(40, 20)
+    depth[:40, :20] = base["depth"].reshape(40, 20)
+    normal[:40, :20] = base["normal"].reshape(40, 20, 3)
+    W, H, L = 480, 320, 320
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas_sized([32], [48], color.reshape(-1), depth.reshape(-1), normal.reshape(-1, 3))
+        r.set_scene(par.scene_default())
+        rgba, gbuf, _ = r.render(par.light_default(), want_gbuf=True)
+    import json, os
+    from conftest import ROOT
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_hashes.json")))["tier1_480x320x320_frame0"]
+    assert sha256(rgba) == g["frame0_pre_overlay_sha256"]
+    assert sha256(gbuf) == g["gbuf0_sha256"]
+
+
+def test_sized_atlas_validation(par):
+    from par_b200 import AABB
+    with par.Renderer(480, 320, 320) as r:
+        with pytest.raises(par.ParError) as e:
+            r.set_atlas_sized([0], [40], np.zeros(0), np.zeros(0), np.zeros((0, 3)))
+        assert e.value.code == -1
+        with pytest.raises(par.ParError) as e:
+            r.set_atlas_sized([4], [4], np.zeros(16), np.full(16, 5000), np.zeros((16, 3)))
+        assert e.value.code == -1  # depth out of range
+        r.set_atlas_sized([16], [32], np.zeros(512), np.zeros(512), np.zeros((512, 3)))
+        r.set_scene(np.array([(10, 0, 10, 17, 10, 10, (0, 0))], AABB))  # extent.x 17 > width 16
+        with pytest.raises(par.ParError) as e:
+            r.render(par.light_default())
+        assert e.value.code == -5 and "entity 0" in str(e.value)
+        r.set_scene(np.array([(10, 0, 10, 16, 20, 13, (0, 0))], AABB))  # ey + ez = 33 > height 32
+        with pytest.raises(par.ParError):
+            r.render(par.light_default())
+        r.set_scene(np.array([(10, 0, 10, 16, 20, 12, (0, 0))], AABB))
+        r.render(par.light_default())
+
+
+def test_culled_entities_are_never_validated(par, oracle):
+    """An entity the reference culls (alternative.cpp:212-219) never has its sprite indexed, so neither
+    its extents nor its sprite id can make the scene bad — only inserted boxes are validated."""
+    from par_b200 import AABB
+    W, H, L = 480, 320, 320
+    boxes = par.scene_default()[:3000].copy()
+    junk = np.array([(5000, 0, 10, 300, 500, 500, (0, 0)),      # off-screen to the right, absurd extents
+                     (10, 0, 9000, 25, 30, 30, (0, 0))], AABB)   # far beyond the view length
+    scene = np.concatenate([boxes, junk])
+    ids = np.zeros(len(scene), np.int32)
+    ids[-2:] = 77  # sprite ids outside the atlas
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(scene, ids)
+        rgba, _ = r.render(par.light_default())
+    ref = oracle.render(W, H, L, np.ascontiguousarray(boxes, oracle.AABB), oracle.light_default())
+    assert np.array_equal(_u32(rgba), _u32(ref["rgba"]))
+
+
+# ------------------------------------------------------------------ round 2: incremental update, pitch, resident frames
+
+def _grid_and_frame(r, lights):
+    rgba, gbuf, st = r.render(lights, want_gbuf=True)
+    count, ids = r.grid()
+    return rgba, gbuf, count, ids, st
+
+
+def test_incremental_update_equals_full_rebuild(par, oracle):
+    """par_update_entities patches the resident scene: after every update the grid (counts + slot
+    order), the G-buffer, the frame and the loader's counters equal those of a fresh par_set_scene of
+    the same boxes — for the reference's own motion (entity 0 under key script D), for entities
+    leaving and re-entering the view, for several entities at once, for overflowing bins, for a
+    sprite change and for more than PAR_MAX_UPDATE entities (device-side full re-bin)."""
+    from par_b200 import AABB
+    W, H, L = 640, 480, 480
+    rng = np.random.default_rng(99)
+    atlas, pal = _random_atlas(rng, 2, 4)
+    boxes, lights = par.scene_default().copy(), par.light_default()
+    dense, _, _ = _random_scene(rng, W, H, L, 6000, 1, cubes=True)  # wraps rings (quirk Q2)
+    boxes[1000:7000] = dense
+    ids = np.zeros(len(boxes), np.int32)
+    with par.Renderer(W, H, L) as inc, par.Renderer(W, H, L) as full:
+        for r in (inc, full):
+            r.set_atlas(atlas, pal)
+        inc.set_scene(boxes, ids)
+
+        def check(tag):
+            full.set_scene(boxes, ids)
+            a, b = _grid_and_frame(inc, lights), _grid_and_frame(full, lights)
+            assert np.array_equal(a[2], b[2]), f"{tag}: counts"
+            live = np.arange(8)[None, :] < a[2][:, None]
+            assert np.array_equal(np.where(live, a[3], -1), np.where(live, b[3], -1)), f"{tag}: slots"
+            assert a[1].tobytes() == b[1].tobytes(), f"{tag}: G-buffer"
+            assert np.array_equal(_u32(a[0]), _u32(b[0])), f"{tag}: frame"
+            assert (a[4]["n_survivors"], a[4]["n_inserts"]) == (b[4]["n_survivors"], b[4]["n_inserts"]), f"{tag}: counters"
+
+        check("initial")
+        for f in range(1, 40):  # the reference's motion: entity 0 walks, light 0 drifts
+            for k in oracle.script_keys("D", f):
+                par.apply_key(k, boxes, lights)
+            inc.update_entities(0, boxes[0:1])
+            if f % 6 == 0:
+                check(f"script D frame {f}")
+        for step, pos in enumerate([(-500, 0, 100), (100, 20, 100), (100, 20, 9000), (300, 40, 200), (300, 40, 200)]):
+            boxes[0]["px"], boxes[0]["py"], boxes[0]["pz"] = pos  # out of view, back in, out along z, back in, unchanged
+            inc.update_entities(0, boxes[0:1])
+            check(f"teleport {step}")
+        for step in range(4):  # several entities, inside the dense part (ring wrap) and at the end of the scene
+            first = [1200, 3000, len(boxes) - 5, 6990][step]
+            n = [8, 3, 5, 8][step]
+            boxes["px"][first:first + n] += rng.integers(-60, 60, n).astype(np.int16)
+            boxes["pz"][first:first + n] += rng.integers(-60, 60, n).astype(np.int16)
+            inc.update_entities(first, boxes[first:first + n])
+            check(f"multi {step}")
+        ids[2000:2004] = 1  # sprite change with the boxes unchanged
+        inc.update_entities(2000, boxes[2000:2004], ids[2000:2004])
+        check("sprites")
+        boxes["py"][4000:4100] += 15  # a big update: uploaded and re-binned on the device
+        inc.update_entities(4000, boxes[4000:4100])
+        check("big")
+        with pytest.raises(par.ParError) as e:
+            inc.update_entities(len(boxes) - 1, boxes[0:2])
+        assert e.value.code == -1
+        bad = boxes[0:1].copy()
+        bad["ex"] = 30
+        inc.update_entities(0, bad)
+        with pytest.raises(par.ParError) as e:
+            inc.render(lights)
+        assert e.value.code == -5
+
+
+def test_pipelined_updates_moving_scene(par, oracle):
+    """par_submit_update: 30 frames of key script D with 16 bytes of scene traffic per frame; every
+    frame equals the synchronous par_set_scene + par_render of the same scene."""
+    W, H, L = 640, 480, 480
+    boxes, lights = par.scene_default(), par.light_default()
+    scenes, light_seq = [], []
+    for f in range(30):
+        for k in oracle.script_keys("D", f):
+            par.apply_key(k, boxes, lights)
+        scenes.append(boxes[0:1].copy())
+        light_seq.append(lights.copy())
+    want = []
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        full = par.scene_default()
+        for f in range(30):
+            full[0] = scenes[f][0]
+            r.set_scene(full)
+            want.append(r.render(light_seq[f])[0].copy())
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(par.scene_default())
+        out = [par.pinned_empty((H, W), par.COLOR) for _ in range(2)]
+        r.set_cursor(0, 0)
+        for f in range(31):
+            if f < 30:
+                r.submit_update(0, scenes[f], light_seq[f], out[f & 1])
+            if f >= 1:
+                st = r.wait_frame()
+                assert st["n_survivors"] > 0 and st["rays"] == W * H * 2
+                assert np.array_equal(_u32(out[(f - 1) & 1]), _u32(want[f - 1])), f"frame {f - 1}"
+        r.submit_update(0, scenes[0][:0], light_seq[3], out[0])  # nothing moves, only the light
+        st = r.wait_frame()
+        assert st["n_survivors"] > 0
+        full[0] = scenes[29][0]
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(full)
+        assert np.array_equal(_u32(out[0]), _u32(r.render(light_seq[3])[0]))
+
+
+@pytest.mark.parametrize("stripes", [1, 3])
+def test_pitched_host_frames(par, stripes):
+    """The blit contract of alternative.cpp:774-788: rows of the host frame `pitch` bytes apart
+    (par_set_output_pitch for par_render / par_submit_frame / par_read_stripes, par_read_frame_pitched);
+    bytes between the rows stay untouched."""
+    W, H, L = 640, 480, 480
+    boxes, lights = par.scene_synthetic(W, H, L, n=1500, n_lights=3)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        want, _ = r.render(lights)
+    pitch = W * 4 + 192
+    got = np.zeros((H, pitch), np.uint8)
+    pads = []
+    for i in range(stripes):
+        kw = dict(stripe_count=stripes, stripe_index=i) if stripes > 1 else {}
+        with par.Renderer(W, H, L, **kw) as r:
+            r.set_atlas()
+            r.set_scene(boxes)
+            r.set_output_pitch(pitch)
+            buf = par.pinned_empty((H, pitch), np.uint8)
+            buf[:] = 0xAB
+            r.render(lights, out=buf)                    # blocking call, pitched
+            sub = par.pinned_empty((H, pitch), np.uint8)
+            sub[:] = 0xAB
+            hb = par.pinned_empty(len(boxes), par.AABB)
+            hb[:] = boxes
+            lib = par.lib()
+            assert lib.par_submit_frame(r._h, hb.ctypes.data, None, len(hb), np.ascontiguousarray(lights).ctypes.data,
+                                        len(lights), sub.ctypes.data) == 0
+            r.wait_frame()
+            assert np.array_equal(buf, sub)
+            own = np.zeros(H, bool)
+            for t in range(i, H // 40, stripes):
+                own[t * 40:t * 40 + 40] = True
+            got[own] = buf[own]
+            assert (buf[~own] == 0xAB).all() and (buf[:, W * 4:] == 0xAB).all()
+            if stripes == 1:
+                whole = par.pinned_empty((H, pitch), np.uint8)
+                whole[:] = 0xCD
+                r.read_frame_pitched(whole, pitch)
+                r.sync()
+                assert np.array_equal(whole[:, :W * 4], want.view(np.uint8).reshape(H, W * 4))
+                assert (whole[:, W * 4:] == 0xCD).all()
+                with pytest.raises(par.ParError):
+                    r.set_output_pitch(W * 4 - 4)
+    assert np.array_equal(got[:, :W * 4], want.view(np.uint8).reshape(H, W * 4))
+
+
+@pytest.mark.parametrize("tile_order", [-1, 1])
+def test_resident_frames_graph_replay(par, tile_order):
+    """par_render_resident: loader + render kernel replayed as CUDA graphs (one per grid generation),
+    with and without the longest-first tile order; every frame equals par_render, also after the
+    lights, the scene or the cursor change in between."""
+    W, H, L = 1280, 720, 720
+    boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
+    with par.Renderer(W, H, L, tile_order=tile_order) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        want, _ = r.render(lights)
+        for k in range(7):
+            r.render_resident(lights)
+            got = r.read_frame()
+            r.sync()
+            assert np.array_equal(_u32(got), _u32(want)), f"replay {k}"
+        lights2 = lights.copy()
+        lights2["x"] += 40
+        want2, _ = r.render(lights2)
+        r.set_cursor(100, 100)
+        for k in range(4):
+            r.render_resident(lights2)
+            got = r.read_frame()
+            r.sync()
+            assert np.array_equal(_u32(got), _u32(want2)), f"lights changed, replay {k}"
+        moved = boxes.copy()
+        moved["px"][:50] += 33
+        r.update_entities(0, moved[:4])
+        r.set_scene(moved)
+        want3, gbuf3, _ = r.render(lights2, want_gbuf=True)
+        for k in range(4):
+            r.render_resident(lights2)
+            got = r.read_frame()
+            r.sync()
+            assert np.array_equal(_u32(got), _u32(want3)), f"scene changed, replay {k}"
+        assert r.cursor_pixel().tobytes() == gbuf3[100, 100].tobytes()
+        assert r.stats()["n_survivors"] > 0
+
+
+def test_two_contexts_share_a_device(par, oracle):
+    """Contexts with different views and atlases on one device do not disturb each other."""
+    rng = np.random.default_rng(5)
+    a_boxes, a_lights, _ = _random_scene(rng, 480, 320, 320, 900, 2)
+    b_boxes, b_lights = par.scene_synthetic(3840, 2160, 2160, n=4000, n_lights=3)
+    atlas, pal = _random_atlas(rng, 6, 4)
+    with par.Renderer(3840, 2160, 2160) as big, par.Renderer(480, 320, 320) as small:
+        big.set_atlas()
+        small.set_atlas(atlas, pal)
+        big.set_scene(b_boxes)
+        ids = rng.integers(0, 6, len(a_boxes)).astype(np.int32)
+        small.set_scene(a_boxes, ids)
+        first, _ = big.render(b_lights)
+        got, _ = small.render(a_lights)
+        again, _ = big.render(b_lights)
+    ref = oracle.render(480, 320, 320, np.ascontiguousarray(a_boxes, oracle.AABB), np.ascontiguousarray(a_lights, oracle.LIGHT),
+                        atlas=np.ascontiguousarray(atlas, oracle.SPRITE), palette=np.ascontiguousarray(pal, oracle.COLOR),
+                        sprite_ids=ids)
+    assert np.array_equal(_u32(got), _u32(ref["rgba"]))
+    assert np.array_equal(_u32(first), _u32(again))
+
+
+def test_many_groups_and_long_columns(par, oracle):
+    """Tiles whose pixels spread over many start bins (columns of floating cubes at all depths, more
+    groups than one pass handles is not reachable at this view, but > 30 are) and bin columns with
+    more entries than one staging chunk holds."""
+    from par_b200 import AABB
+    W, H, L = 200, 2000, 4000
+    rows = []
+    rng = np.random.default_rng(17)
+    for k in range(900):  # cubes stacked along z with rising y: every tile sees dozens of depths
+        rows.append((int(rng.integers(0, 180)), int(rng.integers(0, 1500)), int(rng.integers(0, 3900)), 20, 20, 20, (0, 0)))
+    for k in range(700):  # one bin column crowded along z (7 kept per bin x 100 bins > 256 entries)
+        rows.append((40 + int(rng.integers(0, 20)), 20 * int(rng.integers(0, 3)), 40 * (k % 100) + int(rng.integers(0, 20)), 20, 20, 20, (0, 0)))
+    boxes = np.array(rows, AABB)
+    lights = np.zeros(3, par.LIGHT)
+    lights["x"], lights["y"], lights["z"] = [100, 10, 190], [800, 300, 1500], [500, 2500, 100]
+    got, ref = _render_both(par, oracle, W, H, L, boxes, lights)
+    _assert_frame_equal(got, ref)

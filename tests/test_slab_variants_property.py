@@ -1,6 +1,6 @@
-"""CPU property test of k_shade's three slab-test variants (exact ternaries, fminf/fmaxf, near/far
+"""CPU property test of k_tile's three slab-test variants (exact ternaries, fminf/fmaxf, near/far
 corners) against the oracle's occlusion predicate — the functions are extracted verbatim from
-csrc/shade.cu and csrc/par_device.cuh and compiled for the host (tests/slab_property.cpp)."""
+csrc/tile.cu and csrc/par_device.cuh and compiled for the host (tests/slab_property.cpp)."""
 import os
 import re
 import subprocess
@@ -24,7 +24,7 @@ def _extract(text, start_pat, end_pat):
 def harness(tmp_path_factory, oracle):
     td = tmp_path_factory.mktemp("slab")
     dev = open(os.path.join(CSRC, "par_device.cuh")).read()
-    shade = open(os.path.join(CSRC, "shade.cu")).read()
+    shade = open(os.path.join(CSRC, "tile.cu")).read()
     parts = [_extract(dev, r"^__device__ __forceinline__ float std_min", r"std_max\(float a, float b\) \{[^}]*\}"),
              _extract(shade, r"^__device__ __forceinline__ bool slab_hit_exact", r"^\}"),
              _extract(shade, r"^__device__ __forceinline__ bool slab_hit_fast", r"^\}"),

@@ -1,4 +1,4 @@
-// Property test of the shadow-walk restructuring used by k_shade / k_walk on the CPU.
+// Property test of the shadow-walk restructuring used by k_tile / k_walk on the CPU.
 // TEST INFRASTRUCTURE: built and run by tests/test_walk_property.py.
 //
 // Reference walk (alternative.cpp:399-476, oracle light_visible): per step the six partial advances

@@ -24,12 +24,25 @@ def run(name, W, H, L, boxes, lights, reps=5):
             st["wall_ms"] = (time.perf_counter() - t0) * 1e3
             if best is None or st["ms_total"] < best["ms_total"]:
                 best = st
+        # the production form: loader + render kernel replayed as one graph per grid generation
+        import torch
+        for _ in range(4):
+            r.render_resident(lights)
+        r.sync()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s = torch.cuda.ExternalStream(r.stream())
+        a.record(s)
+        for _ in range(20):
+            r.render_resident(lights)
+        b.record(s)
+        r.sync()
+        best["resident_step_ms"] = round(a.elapsed_time(b) / 20, 4)
         best["config"] = name
         if os.environ.get("PAR_PHASES"):
             r.phase_timing(True)
             r.render_device(lights)
             ph = r.phase_timing(False)
-            extra = {k: ph.pop(k) for k in ("boxes_found", "boxes_kept", "pixel_lights")}
+            extra = {k: ph.pop(k) for k in ("boxes_found", "boxes_kept", "rounds")}
             tot = sum(ph.values()) or 1
             best["phases_pct"] = {k: round(100.0 * v / tot, 1) for k, v in ph.items()}
             best["lists"] = extra

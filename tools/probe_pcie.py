@@ -1,61 +1,59 @@
-"""Developer probe: PCIe copy times that bound the e2e (host scene -> host frame) path."""
-import sys, os, time
+"""Developer probe: H2D time of the 2.6 MB scene while a 33 MB D2H runs on another stream; and
+kernel time of a resident frame while a D2H runs."""
+import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "pixel-art-raytracer_b200"))
 import numpy as np
 import torch
 import par_b200 as par
 
 dev = torch.device("cuda", 0)
-W, H, L = 3840, 2160, 2160
-d_frame = torch.zeros(W * H * 4, dtype=torch.uint8, device=dev)
-h_frame = torch.zeros(W * H * 4, dtype=torch.uint8).pin_memory()
-h_scene = torch.zeros(2596928, dtype=torch.uint8).pin_memory()
-d_scene = torch.zeros(2596928, dtype=torch.uint8, device=dev)
+n_s, n_f = 2596928, 33177600
+hs = torch.from_numpy(par.pinned_empty(n_s, np.uint8)); hs.fill_(1)
+hf = torch.from_numpy(par.pinned_empty(n_f, np.uint8))
+ds = torch.empty(n_s, dtype=torch.uint8, device=dev)
+df = torch.zeros(n_f, dtype=torch.uint8, device=dev)
+s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 
 
-def ev_time(fn, n=20):
-    fn()
+def h2d_time(with_d2h):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(n):
-        fn()
-    b.record()
+    if with_d2h:
+        with torch.cuda.stream(s2):
+            for _ in range(4):
+                hf.copy_(df, non_blocking=True)
+    with torch.cuda.stream(s1):
+        torch.cuda._sleep(200000)  # ~0.1 ms: let the D2H get going
+        a.record(s1)
+        for _ in range(5):
+            ds.copy_(hs, non_blocking=True)
+        b.record(s1)
     torch.cuda.synchronize()
-    return a.elapsed_time(b) / n
+    return a.elapsed_time(b) / 5
 
 
-t = ev_time(lambda: h_frame.copy_(d_frame, non_blocking=True))
-print(f"D2H 33.2 MB pinned: {t:.4f} ms = {33.1776 / t:.1f} GB/s")
-t = ev_time(lambda: d_scene.copy_(h_scene, non_blocking=True))
-print(f"H2D 2.6 MB pinned: {t:.4f} ms = {2.596928 / t:.1f} GB/s")
+print(f"H2D 2.6 MB alone: {h2d_time(False):.4f} ms; beside a running 33 MB D2H: {h2d_time(True):.4f} ms")
 
-boxes, lights = par.scene_default(), par.light_default()
+W, H, L = 3840, 2160, 2160
 ren = par.Renderer(W, H, L)
+ren.set_stream(s1.cuda_stream)
 ren.set_atlas()
-hb = par.pinned_empty(len(boxes), par.AABB)
-hb[:] = boxes
-outs = [par.pinned_empty((H, W), par.COLOR) for _ in range(2)]
-for steps in (20, 100):
-    for i in range(4):
-        ren.submit_frame(hb, lights, outs[i & 1])
-        if i:
-            ren.wait_frame()
-    ren.wait_frame()
+ren.set_scene(par.scene_default())
+lights = par.light_default()
+for with_d2h in (False, True):
+    ren.render_device(lights)
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for i in range(steps + 1):
-        if i < steps:
-            ren.submit_frame(hb, lights, outs[i & 1])
-        if i:
-            st = ren.wait_frame()
+    if with_d2h:
+        with torch.cuda.stream(s2):
+            for _ in range(6):
+                hf.copy_(df, non_blocking=True)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(s1):
+        torch.cuda._sleep(200000)
+        a.record(s1)
+        for _ in range(5):
+            ren.rebuild_grid()
+            ren.render_device(lights)
+        b.record(s1)
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) * 1e3 / steps
-    print(f"pipelined, no flush, {steps} steps: {dt:.4f} ms/frame (last frame submit->done {st['ms_total']:.3f} ms, of which kernels done->frame on host {st['ms_readback']:.3f})")
-ren.set_scene(hb)
-ren.render(lights, out=outs[0])
-t0 = time.perf_counter()
-for i in range(20):
-    ren.set_scene(hb)
-    ren.render(lights, out=outs[0])
-print(f"sync set_scene+render: {(time.perf_counter() - t0) * 1e3 / 20:.4f} ms/frame")
+    print(f"loader+primary+shade {'beside a running D2H' if with_d2h else 'alone'}: {a.elapsed_time(b) / 5:.4f} ms", ren.stats())
