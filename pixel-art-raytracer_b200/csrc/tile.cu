@@ -64,18 +64,25 @@ constexpr int kPix = kBin * kBin;               // 1600 pixels per tile
 constexpr int kPPT = kPix / kT;                 // 10 pixels per thread (rows rsub + 4m)
 constexpr int kHalf = kPPT / 2;                 // pixels per primary pass
 constexpr int kListCap = PAR_TILE_LIST_CAP;     // boxes in the shared list (two float4 each)
-constexpr int kHashBits = 10;
+#ifndef PAR_TILE_HASH_BITS
+#define PAR_TILE_HASH_BITS 10
+#endif
+constexpr int kHashBits = PAR_TILE_HASH_BITS;
 constexpr int kHashSize = 1 << kHashBits;       // de-duplication set
 constexpr int kOccCap = 512;                    // occupied bins found by the walks of one round
 constexpr int kSegMax = 32;                     // (group, light, step range) segments per round
+constexpr int kSegStart = 10;                   // ... of a many-light tile's first round (then adaptive)
 constexpr int kGroupMax = 64;                   // z-groups handled per pass over the tile
-constexpr int kEntryCap = 256;                  // column entries staged at a time (phase P)
+#ifndef PAR_TILE_ENTRY_CAP
+#define PAR_TILE_ENTRY_CAP 256
+#endif
+constexpr int kEntryCap = PAR_TILE_ENTRY_CAP;   // column entries staged at a time (phase P)
 constexpr int kMaxRun = 32;                     // most walk steps per walk-phase thread
 constexpr int kMaxHL = PAR_MAX_VIEW / kBin;     // 320 bins along z at most
-constexpr int kWarps = kT / 32;
 constexpr int kNoGroup = INT_MAX;
+constexpr int kDoneZ = -32768;                  // TileSmem::z of a pixel whose RGBA8 value is final
 constexpr unsigned kEmpty = 0xffffffffu;
-static_assert(kPix % kT == 0 && kT % 32 == 0 && kT % kBin == 0 && kPPT % 2 == 0, "CTA shape");
+static_assert(kPix % kT == 0 && kT % 32 == 0 && kT == 4 * kBin && kPPT % 2 == 0 && kSegMax == 32, "CTA shape");
 static_assert(kHashSize * 3 / 4 >= kListCap, "the hash set must hold a full list");
 
 struct Seg {
@@ -237,6 +244,9 @@ constexpr unsigned kMissColor = 127u | 127u << 8 | 127u << 16;  // alternative.c
 
 }  // namespace
 
+// kChecks: the parity / debug outputs (G-buffer checkpoint, primary-only mode, fp32 intermediates, phase
+// timing) are compiled into a second instantiation; production frames run the one without them.
+template <bool kChecks>
 __global__ void __launch_bounds__(kT, PAR_TILE_MIN_CTAS)
 k_tile(const __grid_constant__ TileParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -250,15 +260,19 @@ k_tile(const __grid_constant__ TileParams p) {
     const int ty = p.tile_row_first + (slot / d.HW) * max(d.stripe_n, 1);
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
     const int n_lights = p.n_lights;
-    const int col = tid % kBin, rsub = tid / kBin;  // the thread's pixels: rows rsub + 4m of column col
+    // The thread's pixels: rows rsub + 4m of column col.  A warp covers 8 adjacent columns (x 4 row
+    // phases), so the x half of the primary hit test — a sprite is narrower than a tile — is uniform
+    // in most warps instead of splitting every warp in two.
+    const int col = tid >> 2, rsub = tid & 3;
     const int i = bx * kBin + col;
+    const bool probe_here = p.probe_x / kBin == bx && p.probe_y / kBin == ty && p.probe_x >= 0;
 
     // Optional barrier-to-barrier phase timing (debug; p.phase_cycles is NULL in production).
     enum { kPhPrimary, kPhGroup, kPhSetup, kPhWalk, kPhGather, kPhShade, kPhTail };
     long long t_mark = 0;
-    if (p.phase_cycles && tid == 0) t_mark = clock64();
+    if (kChecks && p.phase_cycles && tid == 0) t_mark = clock64();
     auto mark = [&](int phase) {
-        if (p.phase_cycles && tid == 0) {
+        if (kChecks && p.phase_cycles && tid == 0) {
             const long long now = clock64();
             atomicAdd(&p.phase_cycles[phase], (unsigned long long)(now - t_mark));
             t_mark = now;
@@ -387,8 +401,8 @@ k_tile(const __grid_constant__ TileParams p) {
                     continue;
                 }
                 const int y = r_w[m] >= 0 ? (wj0 - 4 * m) - r_z[m] : 0;
-                if (p.gbuf) p.gbuf[(size_t)j * d.W + i] = make_int4(r_ent[m], y, r_z[m], r_w[m]);
-                if (i == p.probe_x && j == p.probe_y) {  // cursor probe (mouse_pixel, alternative.cpp:380-382)
+                if (kChecks && p.gbuf) p.gbuf[(size_t)j * d.W + i] = make_int4(r_ent[m], y, r_z[m], r_w[m]);
+                if (probe_here && i == p.probe_x && j == p.probe_y) {  // cursor probe (mouse_pixel, alternative.cpp:380-382)
                     float4 tx = make_float4(0.f, 0.f, 0.f, __uint_as_float(kMissColor));
                     if (r_w[m] >= 0) tx = __ldg(&p.texel_tab[r_w[m]]);
                     const int rec[7] = {__float_as_int(tx.x), __float_as_int(tx.y), __float_as_int(tx.z),
@@ -412,11 +426,16 @@ k_tile(const __grid_constant__ TileParams p) {
         const int pidx = (rsub + 4 * m) * kBin + col;
         const unsigned w = s.w[pidx];
         gz[m] = kNoGroup;
-        if (w == 0xfffffffeu) continue;
+        if (w == 0xfffffffeu) {
+            s.z[pidx] = kDoneZ;
+            continue;
+        }
         if (w == 0xffffffffu) {
             s.w[pidx] = quantise(kMissColor, amb_only);
-        } else if (n_lights == 0 || p.gbuf_only) {
+            s.z[pidx] = kDoneZ;
+        } else if (n_lights == 0 || (kChecks && p.gbuf_only)) {
             s.w[pidx] = quantise(__float_as_uint(__ldg(&p.texel_tab[w]).w), amb_only);
+            s.z[pidx] = kDoneZ;
         } else {
             gz[m] = s.z[pidx] / kBin;  // ray_bin_z (alternative.cpp:727, C division truncates toward zero)
         }
@@ -424,6 +443,10 @@ k_tile(const __grid_constant__ TileParams p) {
 
     // =============================== G + R, kGroupMax groups at a time ===============================
     int g_done = INT_MIN;  // groups <= g_done are finished
+    // Segments a round starts with.  A round that finds more candidate boxes than the de-duplication set
+    // holds keeps only its leading segments — the walks of the others are thrown away — so the budget
+    // follows the candidate density seen in this tile so far.
+    int seg_budget = n_lights > 4 ? kSegStart : kSegMax;
 #pragma unroll 1
     for (;;) {
         // ---- smallest unprocessed group ----
@@ -479,42 +502,63 @@ k_tile(const __grid_constant__ TileParams p) {
             }
         }
         __syncthreads();
-        // ---- pixels per group and bounds of the ray origins (alternative.cpp:720-722): per warp one
-        //      ballot per distinct group, redux for the bounds, one lane does the shared atomics ----
-        int gi[kPPT];
+        // ---- pixels per group and bounds of the ray origins (alternative.cpp:720-722).  Per warp: one
+        //      iteration per distinct group among its 320 pixels; every lane folds its own pixels of that
+        //      group, one redux per quantity, one lane does the shared-memory atomics ----
+        int gi[kPPT], zz[kPPT];
+        unsigned mine0 = 0u, mine1 = 0u;  // groups this thread's pixels belong to
 #pragma unroll
         for (int m = 0; m < kPPT; m++) {
             gi[m] = group_index(gz[m]);
-            const int row = rsub + 4 * m, pidx = row * kBin + col;
-            const int zz = s.z[pidx];
-            // x = column, z from the record, y = world_j - z (quirk Q11: y + z == H - row)
-            const int o3[3] = {i, (short)(d.H - (ty * kBin + row)) - zz, zz};
-            unsigned todo = __ballot_sync(0xffffffffu, gi[m] >= 0);
-            while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const int gl = __shfl_sync(0xffffffffu, gi[m], leader);
-                const unsigned mask = __ballot_sync(0xffffffffu, gi[m] == gl);
-                if (gi[m] == gl) {
-                    int lo3[3], hi3[3];
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        lo3[a] = __reduce_min_sync(mask, o3[a]);
-                        hi3[a] = __reduce_max_sync(mask, o3[a]);
-                    }
-                    if (lane == leader) {
-                        Grp& g = s.grp[gl];
-                        atomicAdd(&g.n, __popc(mask));
-#pragma unroll
-                        for (int a = 0; a < 3; a++) {
-                            atomicMin(&g.omin[a], lo3[a]);
-                            atomicMax(&g.omax[a], hi3[a]);
-                        }
-                    }
-                }
-                todo &= ~mask;
+            zz[m] = s.z[(rsub + 4 * m) * kBin + col];
+            if (gi[m] >= 0) {
+                if (gi[m] < 32) mine0 |= 1u << gi[m];
+                else mine1 |= 1u << (gi[m] - 32);
             }
         }
+        const unsigned warp0 = __reduce_or_sync(0xffffffffu, mine0), warp1 = __reduce_or_sync(0xffffffffu, mine1);
+        const int wj_top = (short)(d.H - (ty * kBin + rsub));  // world_j of pixel m is wj_top - 4m
+        for (int half = 0; half < 2; half++) {
+            unsigned todo = half ? warp1 : warp0;
+            while (todo) {
+                const int g = 32 * half + __ffs(todo) - 1;
+                todo &= todo - 1;
+                int cnt = 0, zlo = INT_MAX, zhi = INT_MIN, ylo = INT_MAX, yhi = INT_MIN;
+#pragma unroll
+                for (int m = 0; m < kPPT; m++)
+                    if (gi[m] == g) {
+                        cnt++;
+                        // x = column, z from the record, y = world_j - z (quirk Q11: y + z == H - row)
+                        const int y = wj_top - 4 * m - zz[m];
+                        zlo = min(zlo, zz[m]);
+                        zhi = max(zhi, zz[m]);
+                        ylo = min(ylo, y);
+                        yhi = max(yhi, y);
+                    }
+                const int xlo = __reduce_min_sync(0xffffffffu, cnt ? i : INT_MAX);
+                const int xhi = __reduce_max_sync(0xffffffffu, cnt ? i : INT_MIN);
+                cnt = __reduce_add_sync(0xffffffffu, cnt);
+                zlo = __reduce_min_sync(0xffffffffu, zlo);
+                zhi = __reduce_max_sync(0xffffffffu, zhi);
+                ylo = __reduce_min_sync(0xffffffffu, ylo);
+                yhi = __reduce_max_sync(0xffffffffu, yhi);
+                if (lane == 0) {
+                    Grp& G = s.grp[g];
+                    atomicAdd(&G.n, cnt);
+                    atomicMin(&G.omin[0], xlo);
+                    atomicMax(&G.omax[0], xhi);
+                    atomicMin(&G.omin[1], ylo);
+                    atomicMax(&G.omax[1], yhi);
+                    atomicMin(&G.omin[2], zlo);
+                    atomicMax(&G.omax[2], zhi);
+                }
+            }
+        }
+        // With one or two groups a round covers (nearly) every pixel of the tile anyway: the shade phase then
+        // takes the pixels in raster order and no per-group lists are built.
+        const bool natural = n_groups <= 2;
         __syncthreads();
+        if (!natural) {
         if (tid < 32) {  // exclusive scan of the group sizes (two groups per lane)
             const int a = tid < n_groups ? s.grp[tid].n : 0, b = tid + 32 < n_groups ? s.grp[tid + 32].n : 0;
             int ia = a, ib = b;
@@ -531,20 +575,29 @@ k_tile(const __grid_constant__ TileParams p) {
             if (tid + 32 < n_groups) s.grp[tid + 32].p0 = s.cursor[tid + 32] = total_a + ib - b;
         }
         __syncthreads();
-#pragma unroll
-        for (int m = 0; m < kPPT; m++) {  // scatter the pixel indices into the per-group lists
-            unsigned todo = __ballot_sync(0xffffffffu, gi[m] >= 0);
+        for (int half = 0; half < 2; half++) {  // scatter the pixel indices into the per-group lists
+            unsigned todo = half ? warp1 : warp0;
             while (todo) {
-                const int leader = __ffs(todo) - 1;
-                const int gl = __shfl_sync(0xffffffffu, gi[m], leader);
-                const unsigned mask = __ballot_sync(0xffffffffu, gi[m] == gl);
+                const int g = 32 * half + __ffs(todo) - 1;
+                todo &= todo - 1;
+                int c = 0;
+#pragma unroll
+                for (int m = 0; m < kPPT; m++) c += (gi[m] == g);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (lane >= o) incl += t;
+                }
                 int base = 0;
-                if (lane == leader) base = atomicAdd(&s.cursor[gl], __popc(mask));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (gi[m] == gl) s.pix[base + __popc(mask & ((1u << lane) - 1u))] = (unsigned short)((rsub + 4 * m) * kBin + col);
-                todo &= ~mask;
+                if (lane == 31) base = atomicAdd(&s.cursor[g], incl);
+                int at = __shfl_sync(0xffffffffu, base, 31) + incl - c;
+#pragma unroll
+                for (int m = 0; m < kPPT; m++)
+                    if (gi[m] == g) s.pix[at++] = (unsigned short)((rsub + 4 * m) * kBin + col);
             }
         }
+        }  // !natural
         // (the barrier at the top of the first round publishes pix and the group table)
         mark(kPhGroup);
 
@@ -552,52 +605,57 @@ k_tile(const __grid_constant__ TileParams p) {
         const int n_seg_total = n_groups * n_lights;
         int s_cur = 0, ka_cur = 0;  // next unprocessed step of segment s_cur
         int kb_try = -1;            // trial end of the first segment (-1 = the whole walk)
-        int nseg_try = kSegMax;
+        int nseg_try = seg_budget;
 #pragma unroll 1
         while (s_cur < n_seg_total) {
             __syncthreads();  // previous round fully consumed (lists, segments, pixel lists complete)
             // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
             const int nseg = min(nseg_try, n_seg_total - s_cur);
-            if (tid < nseg) {
-                const int sidx = s_cur + tid;
-                const int grp = sidx / n_lights, l = sidx - grp * n_lights;
-                const Grp& G = s.grp[grp];
-                const short4 lt = p.lights[l];
-                // light bin, alternative.cpp:729-732 ('/' truncates toward zero)
-                const int lbx = lt.x / kBin, lby = (d.H - lt.y - lt.z) / kBin, lbz = lt.z / kBin;
-                const float dx = (float)lbx - (float)bx, dy = (float)lby - (float)ty, dz = (float)lbz - (float)G.gz;
-                const float big = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
-                Seg& g = s.seg[tid];
-                g.steps = (int)big;  // 0 when big < 1 (then the NaN step is never used)
-                g.sx = dx / big;
-                g.sy = dy / big;
-                g.sz = dz / big;
-                g.light = l;
-                g.grp = grp;
-                g.start = flat_bin(d, bx, ty, G.gz);  // start bin of every pixel of the group (alternative.cpp:724-727)
-                g.ka = tid == 0 ? ka_cur : 0;
-                g.kb = (tid == 0 && kb_try >= 0) ? kb_try : g.steps;
-                g.count = 0;
-                g.fill = 0;
-                g.octant = group_octant(G, lt);
+            if (tid < 32) {  // warp 0: one lane per segment (kSegMax == 32)
+                int my_steps = 0;
+                if (tid < nseg) {
+                    const int sidx = s_cur + tid;
+                    const int grp = sidx / n_lights, l = sidx - grp * n_lights;
+                    const Grp& G = s.grp[grp];
+                    const short4 lt = p.lights[l];
+                    // light bin, alternative.cpp:729-732 ('/' truncates toward zero)
+                    const int lbx = lt.x / kBin, lby = (d.H - lt.y - lt.z) / kBin, lbz = lt.z / kBin;
+                    const float dx = (float)lbx - (float)bx, dy = (float)lby - (float)ty, dz = (float)lbz - (float)G.gz;
+                    const float big = fmaxf(fmaxf(fabsf(dx), fabsf(dy)), fabsf(dz));
+                    Seg& g = s.seg[tid];
+                    g.steps = (int)big;  // 0 when big < 1 (then the NaN step is never used)
+                    g.sx = dx / big;
+                    g.sy = dy / big;
+                    g.sz = dz / big;
+                    g.light = l;
+                    g.grp = grp;
+                    g.start = flat_bin(d, bx, ty, G.gz);  // start bin of every pixel of the group (alternative.cpp:724-727)
+                    g.ka = tid == 0 ? ka_cur : 0;
+                    g.kb = (tid == 0 && kb_try >= 0) ? kb_try : g.steps;
+                    g.count = 0;
+                    g.fill = 0;
+                    g.octant = group_octant(G, lt);
+                    my_steps = g.kb - g.ka;
+                }
+                // run length: about one work item per thread, so the serial part of a walk stays short
+                const int steps = __reduce_add_sync(0xffffffffu, my_steps);
+                const int run = min(kMaxRun, max(1, (steps + kT - 1) / kT));
+                const int my_items = (my_steps + run - 1) / run;
+                int incl = my_items;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if (tid >= o) incl += t;
+                }
+                if (tid < nseg) s.seg[tid].item0 = incl - my_items;
+                if (tid == 31) {
+                    s.n_items = incl;
+                    s.run = run;
+                    s.n_occ = 0;
+                    s.overflow = 0;
+                }
             }
             for (int t = tid; t < kHashSize; t += kT) s.r.hash[t] = kEmpty;
-            __syncthreads();
-            if (tid == 0) {
-                // run length: about one work item per thread, so the serial part of a walk stays short
-                int steps = 0;
-                for (int q = 0; q < nseg; q++) steps += s.seg[q].kb - s.seg[q].ka;
-                const int run = min(kMaxRun, max(1, (steps + kT - 1) / kT));
-                int items = 0;
-                for (int q = 0; q < nseg; q++) {
-                    s.seg[q].item0 = items;
-                    items += (s.seg[q].kb - s.seg[q].ka + run - 1) / run;
-                }
-                s.n_items = items;
-                s.run = run;
-                s.n_occ = 0;
-                s.overflow = 0;
-            }
             __syncthreads();
             mark(kPhSetup);
 
@@ -688,13 +746,10 @@ k_tile(const __grid_constant__ TileParams p) {
             // de-duplication and the shaft cull a segment keeps a small fraction of its candidates,
             // so each of the n_fit segments gets room for min(candidates, kListCap / n_fit) boxes;
             // if one needs more, the round is redone with half the segments.
-            int n_fit = 0;
-            {
-                int total = 0;
-                while (n_fit < nseg && total + s.seg[n_fit].count <= kHashSize * 3 / 4) {
-                    total += s.seg[n_fit].count;
-                    n_fit++;
-                }
+            int n_fit = 0, cand_total = 0;
+            while (n_fit < nseg && cand_total + s.seg[n_fit].count <= kHashSize * 3 / 4) {
+                cand_total += s.seg[n_fit].count;
+                n_fit++;
             }
             if (n_fit == 0 || n_occ > kOccCap) {  // shrink: fewer segments first, then fewer steps of the first one
                 if (nseg > 1) {
@@ -799,7 +854,7 @@ k_tile(const __grid_constant__ TileParams p) {
                 }
                 continue;
             }
-            if (p.phase_cycles && tid == 0) {  // debug: candidate boxes found / kept after de-dup + cull
+            if (kChecks && p.phase_cycles && tid == 0) {  // debug: candidate boxes found / kept after de-dup + cull
                 unsigned long long found = 0, kept = 0;
                 for (int q = 0; q < n_fit; q++) {
                     found += s.seg[q].count;
@@ -813,18 +868,19 @@ k_tile(const __grid_constant__ TileParams p) {
             // F. shade: one lane per pixel of the groups this round touches
             const int grp_first = s.seg[0].grp, grp_last = s.seg[n_fit - 1].grp;
             const int pix0 = s.grp[grp_first].p0, pix1 = s.grp[grp_last].p0 + s.grp[grp_last].n;
+            const int n_slots = natural ? kPix : pix1 - pix0;
             const bool last_seg_done = s.seg[n_fit - 1].kb == s.seg[n_fit - 1].steps;
-            for (int qb = tid - lane; qb < pix1 - pix0; qb += kT) {
-                const int qi = pix0 + qb + lane;
-                const bool valid = qi < pix1;
-                const int pidx = valid ? s.pix[qi] : 0;
+            for (int qb = tid - lane; qb < n_slots; qb += kT) {
+                const int pidx = natural ? qb + lane : (qb + lane < n_slots ? s.pix[pix0 + qb + lane] : 0);
                 const int row = pidx / kBin;
                 const int j = ty * kBin + row, ipx = bx * kBin + (pidx - row * kBin);
                 const int g_z = s.z[pidx], g_ent = s.ent[pidx];
                 const unsigned g_w = s.w[pidx];
                 const int g_y = (short)(d.H - j) - g_z;  // quirk Q11
+                int grp = group_index(g_z / kBin);
+                const bool valid = natural ? (g_z != kDoneZ && grp >= grp_first && grp <= grp_last) : qb + lane < n_slots;
+                if (!valid) grp = grp_first;
                 // the pixel's segments in this round: [qa, qe)
-                const int grp = valid ? group_index(g_z / kBin) : grp_first;
                 const int qa = max(0, grp * n_lights - s_cur), qe = min(n_fit, (grp + 1) * n_lights - s_cur);
                 const bool fresh = grp * n_lights >= s_cur && s.seg[qa].ka == 0;        // light 0 starts here
                 const bool final_round = (grp + 1) * n_lights - s_cur <= n_fit && (grp != grp_last || last_seg_done);
@@ -859,7 +915,7 @@ k_tile(const __grid_constant__ TileParams p) {
                     tz = tz / len;
                     // alternative.cpp:745-747; a term of 0 adds +0 whether visible or not (Q19)
                     const float lam = std_max(0.f, tex.x * tx + tex.y * tyv + tex.z * tz);
-                    if (p.dbg_t && mine && sg.light == p.dbg_light && sg.ka == 0)
+                    if (kChecks && p.dbg_t && mine && sg.light == p.dbg_light && sg.ka == 0)
                         p.dbg_t[(size_t)j * d.W + ipx] = make_float4(tx, tyv, tz, lam);
                     const bool lit_candidate = mine && lam > 0.f;
                     const int n = sg.fill;
@@ -890,9 +946,10 @@ k_tile(const __grid_constant__ TileParams p) {
                 }
                 if (valid && qa < qe) {
                     if (final_round) {
-                        if (p.dbg_factor) p.dbg_factor[(size_t)j * d.W + ipx] = acc + p.ambient;
+                        if (kChecks && p.dbg_factor) p.dbg_factor[(size_t)j * d.W + ipx] = acc + p.ambient;
                         // alternative.cpp:735 / 757-758
                         s.w[pidx] = quantise(__float_as_uint(tex.w), std_min(1.f, acc + p.ambient));
+                        s.z[pidx] = kDoneZ;
                     } else {
                         reinterpret_cast<unsigned*>(p.out)[at] = __float_as_uint(acc) | (shadowed ? 0x80000000u : 0u);
                     }
@@ -909,14 +966,22 @@ k_tile(const __grid_constant__ TileParams p) {
                 ka_cur = s.seg[n_fit - 1].kb;
             }
             kb_try = -1;
-            nseg_try = kSegMax;
+            {   // next round's budget: fill ~7/8 of the set at this round's density, and leave the fullest
+                // segment 25 % headroom in its share of the box list
+                int max_fill = 1;
+                for (int q = 0; q < n_fit; q++) max_fill = max(max_fill, s.seg[q].fill);
+                const int by_set = (kHashSize * 3 / 4 * 7 / 8) * n_fit / max(cand_total, 1);
+                const int by_list = kListCap / (max_fill + max_fill / 4 + 1);
+                seg_budget = max(1, min(kSegMax, min(by_set, by_list)));
+            }
+            nseg_try = seg_budget;
         }
         g_done = gmin + (kGroupMax - 1);
     }
 
     // ---- 16-byte stores of the finished tile rows ----
     __syncthreads();
-    if (!p.gbuf_only) {
+    if (!(kChecks && p.gbuf_only)) {
         for (int v = tid; v < kPix / 4; v += kT) {
             const int row = v / (kBin / 4), j = ty * kBin + row;
             if (j < ra || j >= rb) continue;
@@ -939,14 +1004,19 @@ k_tile(const __grid_constant__ TileParams p) {
 size_t tile_smem_bytes() { return sizeof(TileSmem); }
 
 cudaError_t configure_tile() {
-    return cudaFuncSetAttribute(k_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    cudaError_t e = cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
 }
 
 cudaError_t launch_tile(const TileParams& p, cudaStream_t st) {
     int first, tile_rows;
     owned_tile_rows(p.d, first, tile_rows);
     if (tile_rows <= 0) return cudaSuccess;
-    k_tile<<<tile_rows * p.d.HW, kT, sizeof(TileSmem), st>>>(p);
+    if (p.gbuf || p.gbuf_only || p.dbg_t || p.dbg_factor || p.phase_cycles)
+        k_tile<true><<<tile_rows * p.d.HW, kT, sizeof(TileSmem), st>>>(p);
+    else
+        k_tile<false><<<tile_rows * p.d.HW, kT, sizeof(TileSmem), st>>>(p);
     return cudaGetLastError();
 }
 

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpar_b200.so")
+LIB_PATH = os.environ.get("PAR_B200_LIB") or os.path.join(HERE, "libpar_b200.so")  # (override: A/B builds)
 
 # numpy mirrors of the reference PODs (alternative.cpp:35-38, 619-622; sprites.hpp:5-6, 53-58, 67-71)
 AABB = np.dtype([("px", "<i2"), ("py", "<i2"), ("pz", "<i2"), ("ex", "<i2"), ("ey", "<i2"),

@@ -1,13 +1,19 @@
-# Developer A/B of compile-time variants on one GPU box: builds the library twice and probes each.
-#   VARIANTS="-DPAR_TRIM=0 -DPAR_TRIM=1" CFGS="c2 c3" tools/ab_build.sh
-for v in ${VARIANTS}; do
-  touch pixel-art-raytracer_b200/csrc/shade.cu
-  flags="${v//,/ }"   # commas separate several flags of one variant
-  PAR_NVCC_EXTRA="$flags" pixel-art-raytracer_b200/build_native.sh > /tmp/ab_build.log 2>&1 || { echo "BUILD FAILED for $flags"; tail -5 /tmp/ab_build.log; continue; }
-  echo "== $flags"
-  python tools/probe_gpu.py ${CFGS:-c2 c3 c5} | python -c "
-import sys,json
-for l in sys.stdin:
-    d=json.loads(l); print(d['config'], 'prim', round(d['ms_primary'],3), 'shade', round(d['ms_shade'],3), 'total', round(d['ms_total'],3))
-"
+#!/usr/bin/env bash
+# Developer helper: build a variant of libpar_b200.so with extra nvcc flags into
+# pixel-art-raytracer_b200/build/variants/<name>/libpar_b200.so (travels to the GPU box; select it
+# with PAR_B200_LIB=<path>).   tools/ab_build.sh six "-DPAR_TILE_MIN_CTAS=6 -DPAR_TILE_LIST_CAP=256 ..."
+set -euo pipefail
+name=${1:?variant name}; extra=${2:-}
+root="$(cd "$(dirname "$0")/.." && pwd)"; pkg="$root/pixel-art-raytracer_b200"
+out="$pkg/build/variants/$name"; mkdir -p "$out"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+objs=()
+for src in "$pkg"/csrc/*.cu "$pkg"/host/host_scene.cpp; do
+    obj="$out/$(basename "${src%.*}").o"
+    "$NVCC" -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -fmad=false -Xcompiler -fPIC \
+        -I"$root/include" -I"$pkg/csrc" $extra -c "$src" -o "$obj" &
+    objs+=("$obj")
 done
+wait
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a "${objs[@]}" -o "$out/libpar_b200.so" -ldl
+echo "$out/libpar_b200.so"
