@@ -157,6 +157,7 @@ class FrameRenderer {
         check(par_render(ctx_, reinterpret_cast<const par_light*>(lights.data()),
                          static_cast<int>(lights.size()), reinterpret_cast<par_color*>(p_texture),
                          reinterpret_cast<par_pixel*>(p_pixel_buffer), stats));
+        resident_entities_ = entities.size();
     }
 
     // Throughput form of render_frame: up to two frames in flight.  submit_frame snapshots the
@@ -165,6 +166,8 @@ class FrameRenderer {
     // (allocate it with alloc_frame(): page-locked memory keeps the readback asynchronous).
     template <int N>
     void submit_frame(Entities<N>& entities, const std::vector<Light>& lights, Color* p_texture) {
+        if (in_flight_ >= 2)  // before touching the staging buffers: the older frame may still be uploading from them
+            throw Error(PAR_ERR_STATE, "FrameRenderer::submit_frame: two frames in flight, call wait_frame first");
         update_atlas(entities);
         Staging& st = staging_[next_ & 1];
         const size_t n = static_cast<size_t>(entities.size());
@@ -182,8 +185,34 @@ class FrameRenderer {
                                reinterpret_cast<const par_light*>(lights.data()), static_cast<int>(lights.size()),
                                reinterpret_cast<par_color*>(p_texture)));
         next_++;
+        in_flight_++;
+        resident_entities_ = entities.size();
     }
-    void wait_frame(par_stats* stats = nullptr) { check(par_wait_frame(ctx_, stats)); }
+    // The same when only entities [first, first + count) moved since the previous frame — what the
+    // reference's key handler does to entity 0 (alternative.cpp:641-660): nothing but those records
+    // travels to the GPU and only the bins they touch are rebuilt (par_submit_update).  Falls back to
+    // a full submit_frame when no scene of this size is resident yet.
+    template <int N>
+    void submit_frame_moved(Entities<N>& entities, int first, int count, const std::vector<Light>& lights,
+                            Color* p_texture) {
+        if (resident_entities_ != entities.size() || entities.atlas_dirty) {
+            submit_frame(entities, lights, p_texture);
+            return;
+        }
+        if (in_flight_ >= 2)
+            throw Error(PAR_ERR_STATE, "FrameRenderer::submit_frame_moved: two frames in flight, call wait_frame first");
+        check(par_submit_update(ctx_, first, count, reinterpret_cast<const par_aabb*>(entities.aabbs.data() + first),
+                                entities.sprite_ids.data() + first, reinterpret_cast<const par_light*>(lights.data()),
+                                static_cast<int>(lights.size()), reinterpret_cast<par_color*>(p_texture)));
+        in_flight_++;
+    }
+    void wait_frame(par_stats* stats = nullptr) {
+        check(par_wait_frame(ctx_, stats));
+        in_flight_--;
+    }
+    // Row pitch of the host frames handed to render_frame / submit_frame (alternative.cpp:774-783: the
+    // locked SDL texture has its own pitch); 0 = packed.
+    void set_output_pitch(size_t pitch_bytes) { check(par_set_output_pitch(ctx_, pitch_bytes)); }
 
     // The record under the mouse cursor (mouse_pixel, alternative.cpp:380-382) of the frame
     // most recently completed, for the debug overlay.
@@ -225,6 +254,8 @@ class FrameRenderer {
     par_ctx* ctx_ = nullptr;
     Staging staging_[2];
     unsigned next_ = 0;
+    int in_flight_ = 0;
+    int resident_entities_ = -1;  // size of the scene resident on the device (-1: none)
 };
 
 }  // namespace par

@@ -10,11 +10,20 @@
 // record under the cursor comes from the cursor probe, not from a G-buffer readback.
 // --sync: the blocking render_frame with the whole G-buffer, the reference's call shape.
 //
-//   par_headless [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm out.ppm] [--sync] [--no-hash]
+// Frames after the first send only what moved (FrameRenderer::submit_frame_moved: the scripted keys move
+// entity 0, alternative.cpp:641-660); --full-upload re-sends the whole scene every frame instead, as the
+// reference re-bins it every frame (alternative.cpp:689-693).
+// --ppm-seq DIR writes every finished frame as DIR/frame_NNN.ppm (the frame sink after the path:
+// alternative.cpp:774-788 hands the same bytes to the display); --pitch BYTES renders into host frames
+// with that row pitch, the locked-texture contract of alternative.cpp:774-783.
+//
+//   par_headless [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm out.ppm] [--ppm-seq dir]
+//                [--pitch bytes] [--sync] [--full-upload] [--no-hash]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "par/reference_types.hpp"
@@ -48,7 +57,9 @@ int main(int argc, char** argv) {
     int W = 480, H = 320, L = 320, frames = 1, device = 0;
     char script = 0;
     const char* ppm = nullptr;
-    bool sync = false, hash = true;
+    const char* ppm_seq = nullptr;
+    size_t pitch = 0;
+    bool sync = false, hash = true, full_upload = false;
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--view") && i + 3 < argc) {
             W = atoi(argv[++i]);
@@ -62,12 +73,19 @@ int main(int argc, char** argv) {
             device = atoi(argv[++i]);
         } else if (!strcmp(argv[i], "--ppm") && i + 1 < argc) {
             ppm = argv[++i];
+        } else if (!strcmp(argv[i], "--ppm-seq") && i + 1 < argc) {
+            ppm_seq = argv[++i];
+        } else if (!strcmp(argv[i], "--pitch") && i + 1 < argc) {
+            pitch = static_cast<size_t>(atoll(argv[++i]));
+        } else if (!strcmp(argv[i], "--full-upload")) {
+            full_upload = true;
         } else if (!strcmp(argv[i], "--sync")) {
             sync = true;
         } else if (!strcmp(argv[i], "--no-hash")) {  // frame rate of the loop without the checker's FNV pass
             hash = false;
         } else {
-            fprintf(stderr, "usage: %s [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm f] [--sync] [--no-hash]\n", argv[0]);
+            fprintf(stderr, "usage: %s [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm f] [--ppm-seq dir] "
+                            "[--pitch bytes] [--sync] [--full-upload] [--no-hash]\n", argv[0]);
             return 2;
         }
     }
@@ -79,8 +97,36 @@ int main(int argc, char** argv) {
 
         par::FrameRenderer renderer(W, H, L, device);
         const size_t px = static_cast<size_t>(W) * H;
-        par::Color* texture[2] = {par::FrameRenderer::alloc_frame(W, H), par::FrameRenderer::alloc_frame(W, H)};
+        const size_t row_bytes = static_cast<size_t>(W) * sizeof(par::Color);
+        if (pitch && (pitch < row_bytes || pitch % 4)) {
+            fprintf(stderr, "--pitch must be a multiple of 4 and at least %zu\n", row_bytes);
+            return 2;
+        }
+        const size_t stride = pitch ? pitch : row_bytes;  // bytes between rows of a host frame
+        if (pitch) renderer.set_output_pitch(pitch);
+        auto alloc_texture = [&]() {
+            void* p = par_alloc_host(stride * H);
+            if (!p) throw par::Error(PAR_ERR_OUT_OF_MEMORY, par_last_error());
+            memset(p, 0, stride * H);
+            return static_cast<par::Color*>(p);
+        };
+        par::Color* texture[2] = {alloc_texture(), alloc_texture()};
         par::Color* last = texture[0];
+        std::vector<par::Color> packed(pitch ? px : 0);  // pitched frames are packed for overlay / hash / PPM
+        auto write_ppm = [&](const char* path, const par::Color* frame) {
+            FILE* fp = fopen(path, "wb");
+            if (!fp) return false;
+            fprintf(fp, "P6\n%d %d\n255\n", W, H);
+            std::vector<unsigned char> rgb(px * 3);
+            for (size_t i = 0; i < px; i++) {
+                rgb[3 * i] = frame[i].red;
+                rgb[3 * i + 1] = frame[i].green;
+                rgb[3 * i + 2] = frame[i].blue;
+            }
+            fwrite(rgb.data(), 1, rgb.size(), fp);
+            fclose(fp);
+            return true;
+        };
         auto apply_script = [&](int f) {
             if (script == 'C' || script == 'D') {
                 par_aabb* player = reinterpret_cast<par_aabb*>(&entities.aabbs[0]);
@@ -90,9 +136,19 @@ int main(int argc, char** argv) {
             }
         };
         auto finish = [&](int f, par::Color* tex, const par::Pixel& under, const par::Light& light) {
+            if (pitch) {  // the consumer's view of a pitched frame: its W * 4 bytes of every row
+                for (int j = 0; j < H; j++)
+                    memcpy(&packed[static_cast<size_t>(j) * W], reinterpret_cast<const char*>(tex) + j * stride, row_bytes);
+                tex = packed.data();
+            }
             par_draw_overlay_at(W, H, reinterpret_cast<const par_pixel*>(&under),
                                 reinterpret_cast<const par_light*>(&light), 0, reinterpret_cast<par_color*>(tex));
             if (hash) printf("%03d %016llx\n", f, fnv1a64(reinterpret_cast<const unsigned char*>(tex), px * 4));
+            if (ppm_seq) {
+                char name[32];
+                snprintf(name, sizeof name, "/frame_%03d.ppm", f);
+                if (!write_ppm((std::string(ppm_seq) + name).c_str(), tex)) throw par::Error(PAR_ERR_INVALID_ARG, "cannot write into the --ppm-seq directory");
+            }
             last = tex;
         };
         double gpu_ms = 0;
@@ -113,7 +169,10 @@ int main(int argc, char** argv) {
                 if (f < frames) {
                     apply_script(f);
                     light_of[f & 1] = lights[0];
-                    renderer.submit_frame(entities, lights, texture[f & 1]);
+                    if (full_upload || f == 0)
+                        renderer.submit_frame(entities, lights, texture[f & 1]);
+                    else  // the scripted keys move entity 0 only (alternative.cpp:641-660)
+                        renderer.submit_frame_moved(entities, 0, 1, lights, texture[f & 1]);
                 }
                 if (f >= 1) {
                     par_stats st{};
@@ -126,18 +185,14 @@ int main(int argc, char** argv) {
         const double wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         fprintf(stderr, "%d frame(s) %dx%dx%d, %s: %.3f ms/frame wall (scene update, upload, render, readback, overlay%s) "
                         "= %.1f frames/s; %.3f ms/frame %s\n", frames, W, H, L,
-                sync ? "blocking render_frame + G-buffer" : "pipelined submit_frame/wait_frame + cursor probe",
+                sync ? "blocking render_frame + G-buffer"
+                     : full_upload ? "pipelined submit_frame/wait_frame (whole scene uploaded per frame) + cursor probe"
+                                   : "pipelined submit_frame_moved/wait_frame (16-byte scene update per frame) + cursor probe",
                 wall_ms / frames, hash ? ", FNV hash" : "", 1e3 * frames / wall_ms, gpu_ms / frames,
                 sync ? "on the GPU (loader + kernels)" : "submit -> frame on the host (latency)");
-        if (ppm) {
-            FILE* fp = fopen(ppm, "wb");
-            if (!fp) return 1;
-            fprintf(fp, "P6\n%d %d\n255\n", W, H);
-            for (size_t i = 0; i < px; i++) fwrite(&last[i], 1, 3, fp);
-            fclose(fp);
-        }
-        par::FrameRenderer::free_frame(texture[0]);
-        par::FrameRenderer::free_frame(texture[1]);
+        if (ppm && !write_ppm(ppm, last)) return 1;
+        par_free_host(texture[0]);
+        par_free_host(texture[1]);
     } catch (const par::Error& e) {
         fprintf(stderr, "par error %d: %s\n", e.code, e.what());
         return 1;

@@ -6,6 +6,7 @@ tests check that the device path renders the same scenes bit-exactly.
 
     python tests/golden/make_workload_ops.py c1 c4 c2 c3      # c5 / c5b take many minutes
 """
+import hashlib
 import json
 import os
 import sys
@@ -41,6 +42,7 @@ def main():
         res[name] = {"view": [W, H, L], "n_entities": int(len(boxes)), "n_lights": int(len(lights)),
                      "rays": W * H * (1 + len(lights)), "counters": r["counters"],
                      "algorithmic_ops": r["ops"], "frame_fnv1a64": "%016x" % O.fnv1a64(r["rgba"]),
+                     "frame_sha256": hashlib.sha256(r["rgba"].tobytes()).hexdigest(),
                      "gbuf_fnv1a64": "%016x" % O.fnv1a64(r["gbuf"]),      # raw Pixel[] bytes (28 B each)
                      "texel_fnv1a64": "%016x" % O.fnv1a64(r["texel"]),    # int32 texel-index plane, -1 = miss
                      "oracle_seconds_container": round(time.time() - t, 2)}

@@ -163,3 +163,40 @@ def test_headless_driver_full_c4_sequence(par, golden):
                          check=True, capture_output=True)
     print(res.stderr.decode())  # frames/s of the sequence (shown with pytest -s / on failure)
     assert hashlib.sha256(res.stdout).hexdigest() == golden["tier1_1920x1080x1080_scriptD_240"]["hash_file_sha256"]
+
+
+@pytest.mark.parametrize("extra", [["--full-upload"], ["--pitch", "2048"], ["--pitch", "2048", "--full-upload"]])
+def test_headless_driver_upload_modes_and_pitched_frames(par, golden, extra):
+    """The same 40 frames of key script C when the whole scene is re-sent every frame (the reference's
+    shape, alternative.cpp:689-693) instead of the 16-byte update, and when the host frames have a row
+    pitch wider than W * 4 (locked-texture contract, alternative.cpp:774-783): same hashes."""
+    exe = os.path.join(PKG, "build", "par_headless")
+    if not os.path.exists(exe):
+        pytest.skip("par_headless not built")
+    out = subprocess.run([exe, "--frames", "40", "--script", "C"] + extra, check=True, capture_output=True, text=True).stdout
+    got = [ln.split()[1] for ln in out.splitlines()]
+    assert got == golden["tier0_480x320x320_scriptC_240"]["fnv1a64"][:40]
+
+
+def test_headless_driver_writes_the_frame_sequence(par, golden, tmp_path):
+    """--ppm-seq: every finished frame (overlay included) lands as DIR/frame_NNN.ppm; the RGB bytes of each
+    file are the frame whose FNV-1a-64 the driver printed (frame sink, alternative.cpp:774-788)."""
+    exe = os.path.join(PKG, "build", "par_headless")
+    if not os.path.exists(exe):
+        pytest.skip("par_headless not built")
+    W, H, n = 480, 320, 12
+    out = subprocess.run([exe, "--frames", str(n), "--script", "C", "--ppm-seq", str(tmp_path)],
+                         check=True, capture_output=True, text=True).stdout
+    hashes = [ln.split()[1] for ln in out.splitlines()]
+    assert hashes == golden["tier0_480x320x320_scriptC_240"]["fnv1a64"][:n]
+    files = sorted(os.listdir(tmp_path))
+    assert files == [f"frame_{f:03d}.ppm" for f in range(n)]
+    header = f"P6\n{W} {H}\n255\n".encode()
+    seen = set()
+    for f in files:
+        raw = open(os.path.join(tmp_path, f), "rb").read()
+        assert raw.startswith(header) and len(raw) == len(header) + W * H * 3
+        seen.add(raw)
+        rgb = np.frombuffer(raw[len(header):], np.uint8).reshape(H, W, 3)
+        assert (rgb[0, 0] == (255, 0, 0)).all()  # the red overlay line starts under the cursor (0, 0)
+    assert len(seen) == n  # the player moves every frame
