@@ -326,7 +326,8 @@ void par_palette_default(par_color out[4]);
  * (alternative.cpp:624-626).  Returns the entity count; writes at most cap records. */
 int par_scene_default(par_aabb* out, int cap);
 void par_light_default(par_light* out);
-/* SURVEY.md §8(d) synthetic recipe (C3/C5): n cubes + n_lights lights from splitmix64. */
+/* SURVEY.md §8(d) synthetic recipe (C3/C5): n cubes + n_lights lights from splitmix64.  Stated for
+ * width, length > 20 and height > 600; smaller views clamp the affected coordinate range to 1. */
 void par_scene_synthetic(int width, int height, int length, uint64_t seed, int n,
                          par_aabb* out_aabbs, int n_lights, par_light* out_lights);
 /* Key semantics of alternative.cpp:641-681 on entity 0 / light 0.  key: 'L','R' arrows,
@@ -339,6 +340,9 @@ void par_draw_overlay(int width, int height, const par_pixel* gbuf, const par_li
                       int cursor_x, int cursor_y, par_color* frame);
 void par_draw_overlay_at(int width, int height, const par_pixel* under_cursor, const par_light* light,
                          int cursor_x, par_color* frame);
+/* FNV-1a-64 over a byte range — the per-frame hash of the 240-frame golden sequences,
+ * taken over the RGBA bytes handed to the frame sink (alternative.cpp:774-788). */
+uint64_t par_fnv1a64(const void* data, size_t bytes);
 
 #ifdef __cplusplus
 } /* extern "C" */

@@ -963,6 +963,7 @@ static int enqueue_resident_frame(par_ctx* c, const par_light* lights, int n_lig
         if (their_arrive.n) k_flag_signal<<<1, 32, 0, c->stream>>>(their_arrive, c->d_seq + 0, 0u);
         if (mine_arrive.n) k_flag_wait<<<1, 32, 0, c->stream>>>(mine_arrive, c->d_seq + 2, 1u, 1, c->h_exchange_timeout);
         PAR_CUDA(cudaGetLastError());
+        c->launches_frame += (their_credit.n > 0) + (mine_credit.n > 0) + (their_arrive.n > 0) + (mine_arrive.n > 0);
     }
     return PAR_OK;
 }

@@ -121,19 +121,22 @@ void par_light_default(par_light* out) {  // alternative.cpp:624-626 with 480/32
 
 void par_scene_synthetic(int width, int height, int length, uint64_t seed, int n,
                          par_aabb* out_aabbs, int n_lights, par_light* out_lights) {
+    // The recipe is stated for the 4K / 8K views; for views too small for its ranges (width or length
+    // <= 20, height <= 600) the modulus is clamped to 1 instead of dividing by zero or wrapping.
+    const auto span = [](int v) { return static_cast<uint64_t>(v > 1 ? v : 1); };
     SplitMix64 rng{seed};
     SceneWriter w{out_aabbs, n};
     for (int e = 0; e < n; ++e) {
-        const int x = static_cast<int>(rng.next() % static_cast<uint64_t>(width - 20));
+        const int x = static_cast<int>(rng.next() % span(width - 20));
         const int y = static_cast<int>(rng.next() % 200u);
-        const int z = static_cast<int>(rng.next() % static_cast<uint64_t>(length - 20));
+        const int z = static_cast<int>(rng.next() % span(length - 20));
         w.cube(x, y, z);
     }
     for (int l = 0; l < n_lights; ++l) {
         par_light& lt = out_lights[l];
-        lt.x = static_cast<int16_t>(rng.next() % static_cast<uint64_t>(width));
+        lt.x = static_cast<int16_t>(rng.next() % span(width));
         lt.y = static_cast<int16_t>(40 + rng.next() % 400u);
-        lt.z = static_cast<int16_t>(rng.next() % static_cast<uint64_t>(height - 600));
+        lt.z = static_cast<int16_t>(rng.next() % span(height - 600));
         lt.radius = 10;
     }
 }
@@ -189,6 +192,18 @@ void par_draw_overlay_at(int width, int height, const par_pixel* under_cursor, c
             y += dir_y;
         }
     }
+}
+
+// FNV-1a-64 of a byte range: the per-frame hash of the 240-frame goldens, taken over the
+// W*H*4 RGBA bytes a host hands to its frame sink (alternative.cpp:774-788).
+uint64_t par_fnv1a64(const void* data, size_t bytes) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    uint64_t h = 1469598103934665603ull;
+    for (size_t k = 0; k < bytes; k++) {
+        h ^= p[k];
+        h *= 1099511628211ull;
+    }
+    return h;
 }
 
 }  // extern "C"

@@ -46,7 +46,7 @@ EXPORTS = ["par_create", "par_destroy", "par_last_error", "par_version", "par_se
            "par_exchange_setup",
            "par_sprite_tile_floor", "par_palette_default", "par_scene_default",
            "par_light_default", "par_scene_synthetic", "par_apply_key", "par_draw_overlay",
-           "par_draw_overlay_at", "par_set_cursor", "par_cursor_pixel"]
+           "par_draw_overlay_at", "par_set_cursor", "par_cursor_pixel", "par_fnv1a64"]
 
 
 class Config(C.Structure):
@@ -157,6 +157,8 @@ def lib():
         L.par_draw_overlay.restype = None
         L.par_draw_overlay_at.argtypes = [i32, i32, vp, vp, i32, vp]
         L.par_draw_overlay_at.restype = None
+        L.par_fnv1a64.argtypes = [vp, C.c_size_t]
+        L.par_fnv1a64.restype = C.c_uint64
         L.par_set_cursor.argtypes = [vp, i32, i32]
         L.par_cursor_pixel.argtypes = [vp, vp]
         _lib = L
@@ -220,6 +222,12 @@ def draw_overlay_at(W, H, under_cursor, lights, frame, cx=0) -> None:
     """Overlay from the single record under the cursor (Renderer.cursor_pixel())."""
     under = np.ascontiguousarray(under_cursor, PIXEL).reshape(1)
     lib().par_draw_overlay_at(W, H, _p(under), _p(lights), cx, _p(frame))
+
+
+def fnv1a64(arr) -> int:
+    """FNV-1a-64 of an array's bytes (the per-frame hash of the 240-frame goldens)."""
+    a = np.ascontiguousarray(arr)
+    return int(lib().par_fnv1a64(a.ctypes.data, a.nbytes))
 
 
 def pinned_empty(shape, dtype) -> np.ndarray:

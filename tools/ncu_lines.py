@@ -55,6 +55,8 @@ def main():
     ap.add_argument("--outer", action="store_true", help="attribute inlined code to its call site")
     ap.add_argument("--sass", action="store_true", help="list the hottest SASS instructions too")
     ap.add_argument("--by", default="samples", choices=["samples", "inst"], help="sort key")
+    ap.add_argument("--symbol", default=None, help="substring of the mangled name in the cubin (default: the kernel "
+                                                   "name), e.g. k_tileILb0 for k_tile<false>")
     a = ap.parse_args()
     raw = subprocess.run(["ncu", "-i", a.report, "--page", "source", "--csv", "-k", "regex:" + a.kernel], check=True,
                          capture_output=True, text=True).stdout
@@ -64,7 +66,7 @@ def main():
     col = {name: h.index(name) for name in ("Address", "Source", "# Samples", "Instructions Executed",
                                             "Thread Instructions Executed")}
     stall_cols = [(i, n) for i, n in enumerate(h) if n.startswith("stall_") and "Not Issued" not in n]
-    table = line_table(a.stem, a.kernel)
+    table = line_table(a.stem, a.symbol or a.kernel)
     base = None
     per_line = collections.defaultdict(lambda: [0, 0, 0, collections.Counter()])
     sass = []

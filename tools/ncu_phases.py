@@ -1,23 +1,29 @@
 #!/usr/bin/env python
-"""Developer tool: aggregate a k_shade ncu profile by kernel phase (markers found in shade.cu)."""
+"""Developer tool: aggregate a k_tile ncu profile by kernel phase (markers found in tile.cu)."""
 import re
 import subprocess
 import sys
 
 rep = sys.argv[1]
-src = open("pixel-art-raytracer_b200/csrc/shade.cu").read().splitlines()
+src = open("pixel-art-raytracer_b200/csrc/tile.cu").read().splitlines()
 marks = [("slab tests (device functions)", r"^__device__ __forceinline__ bool slab_hit_exact"),
-         ("block scan / helpers", r"^// Block-wide exclusive scan"),
-         ("prologue + tile load", r"^k_shade\("),
-         ("find group", r"---- next group"),
-         ("compact group", r"---- compact the group"),
-         ("fetch precomputed lists", r"fast path: the walks of this group"),
-         ("round setup (A/B)", r"// A\. describe the trial segments"),
-         ("walk (C)", r"// C\. phase 1"),
-         ("decide (D)", r"// D\. how many leading segments"),
-         ("gather (E)", r"// E\. phase 2"),
-         ("shade (F)", r"// F\. phase 3"),
-         ("advance + store", r"// advance past the processed segments")]
+         ("box store / octant / quantise helpers", r"^// Box -> shared list slot"),
+         ("prologue", r"^k_tile\(const __grid_constant__"),
+         ("P: column counts + scan", r"P\. primary rays ====="),
+         ("P: entry gather", r"gather the chunk's entries"),
+         ("P: per-pixel walk", r"// per-pixel walk: the entry list"),
+         ("P: records", r"// records of this pass"),
+         ("miss pixels + group keys", r"---- miss pixels"),
+         ("G: find groups", r"---- smallest unprocessed group"),
+         ("G: group bounds", r"---- pixels per group and bounds"),
+         ("G: scatter into lists", r"exclusive scan of the group sizes"),
+         ("R: round setup (A)", r"// A\. describe the trial segments"),
+         ("R: walk (C)", r"// C\. walk\."),
+         ("R: decide (D)", r"// D\. how many leading segments"),
+         ("R: gather (E)", r"// E\. gather"),
+         ("R: shade (F)", r"// F\. shade"),
+         ("R: advance", r"// advance past the processed segments"),
+         ("tail: 16-byte stores (+ peers)", r"---- 16-byte stores of the finished tile rows")]
 starts = []
 for name, pat in marks:
     for i, ln in enumerate(src, 1):
@@ -29,8 +35,8 @@ starts.sort()
 
 def phase(f, l):
     if f == "shaft.cuh":
-        return "gather (E)"
-    if f != "shade.cu":
+        return "R: gather (E)"
+    if f != "tile.cu":
         return "inlined: " + f
     name = "file header"
     for s, n in starts:
@@ -39,7 +45,7 @@ def phase(f, l):
     return name
 
 
-out = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "shade", "k_shade", "--top", "2000", "--by", "inst"],
+out = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "tile", "k_tile", "--symbol", sys.argv[2] if len(sys.argv) > 2 else "k_tileILb0", "--top", "2000", "--by", "inst"],
                      capture_output=True, text=True).stdout.splitlines()
 print(out[0])
 agg = {}

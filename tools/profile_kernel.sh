@@ -3,27 +3,28 @@
 # per-phase tables.  Step 1 runs on the GPU box (under gpurun, ONE GPU, only after the same probe
 # has exited 0 without ncu); step 2 runs anywhere (no GPU needed), against the SAME build.
 #
-#   gpurun --timeout 600 -- 'tools/profile_kernel.sh capture c2 k_shade r02_shade_c2'
-#   tools/profile_kernel.sh report r02_shade_c2 shade k_shade     # -> profiles/<tag>_lines.txt, _metrics.txt
+#   gpurun --timeout 600 -- 'tools/profile_kernel.sh capture c2 k_tile r02_tile_c2'
+#   tools/profile_kernel.sh report r02_tile_c2 tile k_tile     # -> profiles/<tag>_lines.txt, _metrics.txt
 set -euo pipefail
 cmd=${1:?capture|report}
 case "$cmd" in
 capture)
     wl=${2:?workload}; kernel=${3:?kernel name}; tag=${4:?tag}
     python tools/probe_gpu.py "$wl" > "gpurun_out/${tag}_probe.log" 2>&1   # must pass on its own first
+    python -c "import bench; print(bench.kernel_source_sha())" > "gpurun_out/${tag}.srcsha"   # keys the capture (bench.py)
     ncu --set full --clock-control none --import-source on -k "regex:${kernel}" -c 1 -f \
         -o "gpurun_out/${tag}" python tools/probe_gpu.py "$wl" > "gpurun_out/${tag}_ncu.log" 2>&1
     ls -la "gpurun_out/${tag}.ncu-rep"
     ;;
 report)
-    tag=${2:?tag}; stem=${3:?cubin stem, e.g. shade}; kernel=${4:?kernel name}
+    tag=${2:?tag}; stem=${3:?cubin stem, e.g. tile}; kernel=${4:?kernel name}   # [5: mangled-name substring, e.g. k_tileILb0]
     rep="gpurun_out/${tag}.ncu-rep"
     mkdir -p profiles
     {
         echo "# ${tag} — ${kernel}, ncu --set full"
         python tools/ncu_phases.py "$rep" 2>/dev/null || true
         echo
-        python tools/ncu_lines.py "$rep" "$stem" "$kernel" --top 40 --by inst
+        python tools/ncu_lines.py "$rep" "$stem" "$kernel" --symbol "${5:-$kernel}" --top 40 --by inst
     } > "profiles/${tag}_lines.txt"
     ncu -i "$rep" --page raw --csv -k "regex:${kernel}" > "gpurun_out/${tag}_raw.csv" 2>/dev/null
     python - "$tag" <<'PY'
