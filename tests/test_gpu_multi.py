@@ -200,3 +200,56 @@ def test_headless_driver_writes_the_frame_sequence(par, golden, tmp_path):
         rgb = np.frombuffer(raw[len(header):], np.uint8).reshape(H, W, 3)
         assert (rgb[0, 0] == (255, 0, 0)).all()  # the red overlay line starts under the cursor (0, 0)
     assert len(seen) == n  # the player moves every frame
+
+
+@pytest.mark.parametrize("root", [-1, 0, 1])
+def test_resident_frames_with_flag_exchange(par, root):
+    """par_render_resident + par_exchange_setup on two GPUs: the render kernels store their stripes into the
+    consumers' frames, arrival / credit flags in the frame footers order the frames (no collective, no host
+    round trip).  Frames replayed from the captured graphs, frames after a light change (graphs re-captured)
+    and after an entity update must all leave the 1-GPU frame on every consumer."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    W, H, L = 1280, 720, 720
+    boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
+    with par.Renderer(W, H, L) as ref, \
+            par.Renderer(W, H, L, device=0, stripe_count=2, stripe_index=0) as a, \
+            par.Renderer(W, H, L, device=1, stripe_count=2, stripe_index=1) as b:
+        ref.set_atlas()
+        a.peer_set(1, b.device_frame())
+        b.peer_set(0, a.device_frame())
+        for r in (a, b):
+            r.set_atlas()
+            r.set_scene(boxes)
+            r.exchange_setup(root)
+
+        def check(tag):
+            ref.set_scene(boxes)
+            want, _ = ref.render(lights)
+            for r in (a, b):
+                r.sync()
+            for idx, r in enumerate((a, b)):
+                if root in (-1, idx):
+                    got = r.read_frame()
+                    r.sync()
+                    assert np.array_equal(want.view(np.uint32), got.view(np.uint32)), f"{tag}: rank {idx}"
+
+        for _ in range(7):  # first frames run plainly / are captured, the later ones are graph replays
+            a.render_resident(lights)
+            b.render_resident(lights)
+        check("replayed frames")
+        lights = lights.copy()
+        lights["x"] += 35
+        lights["z"] += 20
+        for _ in range(3):
+            b.render_resident(lights)  # the enqueue order between the ranks must not matter
+            a.render_resident(lights)
+        check("after moving the lights")
+        boxes = boxes.copy()
+        boxes["px"][:4] += 60
+        for r in (a, b):
+            r.update_entities(0, boxes[:4])
+        for _ in range(2):
+            a.render_resident(lights)
+            b.render_resident(lights)
+        check("after an entity update")
