@@ -23,7 +23,8 @@ Rays are reference-equivalent rays: W*H*(1 + n_lights) per frame (SURVEY.md §8d
              reference-equivalent figure (SURVEY.md §8d weights x oracle counters / time / peak): how
              much of the reference's work the kernel legally never does.
 `scale_8k` : the 7680x4320 workloads of BASELINE.json configs[4] (c5b: 40k sprites, c5: 10k sprites,
-             16 lights) timed the same way as `value`, at every N, in the same line.
+             16 lights) timed the same way as `value`, at every N, in the same line; `c3_series` likewise for
+             configs[2] (10k sprites + 16 lights at 3840x2160).
 `c4_sequence`: configs[3] — 240 frames of key script D at 1920x1080 through the pipelined calls, with
              the per-frame hash file checked against the real reference's (N=1 only).
 """
@@ -343,8 +344,8 @@ class Job:
             dist.barrier()
 
 
-def series_8k(env, args, ops_tab, name):
-    """The device-resident step of an 8K workload (BASELINE.json configs[4]) at this N."""
+def series_other(env, args, ops_tab, name):
+    """The device-resident step of another BASELINE.json workload (configs[2]: c3; configs[4]: c5b / c5) at this N."""
     import torch
     import torch.distributed as dist
     job = Job(env, name, args.exchange)
@@ -659,10 +660,14 @@ def ours(args):
     if not args.no_scale_8k and args.workload not in ("c5", "c5b"):
         scale_8k = {}
         for name in ("c5b", "c5"):
-            r8 = series_8k(env, args, ops_tab, name)
+            r8 = series_other(env, args, ops_tab, name)
             if rank == 0:
                 scale_8k[name] = r8
             trace(f"8K series {name} done")
+    # ---- BASELINE.json configs[2]: dense synthetic scene, 16 lights with shadow rays, at 3840x2160 ----
+    c3 = None
+    if not args.no_scale_8k and args.workload != "c3":
+        c3 = series_other(env, args, ops_tab, "c3")
 
     if rank != 0:
         if world > 1:
@@ -761,6 +766,8 @@ def ours(args):
     }
     if scale_8k is not None:
         line["scale_8k"] = scale_8k
+    if c3 is not None:
+        line["c3_series"] = c3
     if c4 is not None:
         line["c4_sequence"] = c4
     if world == 1 and not args.no_cpu_baseline:
@@ -805,7 +812,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-budget", type=float, default=60.0, help="seconds of CPU work for the CPU legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-scale-8k", action="store_true", help="skip the 8K series (scale_8k)")
+    ap.add_argument("--no-scale-8k", action="store_true", help="skip the 8K series (scale_8k) and the c3 series")
     ap.add_argument("--no-c4", action="store_true", help="skip the 240-frame sequence (c4_sequence)")
     ap.add_argument("--steps-8k", type=int, default=20, help="timed steps of each 8K series")
     ap.add_argument("--exchange", default="root", choices=["root", "peer", "nccl"],

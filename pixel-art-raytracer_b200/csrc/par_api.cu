@@ -10,6 +10,8 @@
 #include <new>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges cost a null check unless a profiler injected itself
+
 #include "par/par.h"
 #include "par_kernels.cuh"
 
@@ -133,6 +135,14 @@ static int fail(int code, const char* fmt, const char* a = "", const char* b = "
     } while (0)
 
 constexpr int kMaxChunks = 8;  // row chunks of the pipelined readback in par_render
+
+// NVTX range over the host side of an entry point (shows up in Nsight Systems / ncu --nvtx timelines).
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct par_ctx {
     par_config cfg;
@@ -645,10 +655,12 @@ static int set_scene_impl(par_ctx* c, const par_aabb* aabbs, const int32_t* spri
 }
 
 int par_set_scene(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n) {
+    NvtxRange nvtx("par_set_scene");
     return set_scene_impl(c, aabbs, sprite_ids, n, nullptr);
 }
 
 int par_rebuild_grid(par_ctx* c) {
+    NvtxRange nvtx("par_rebuild_grid");
     if (!c) return fail(PAR_ERR_INVALID_ARG, "par_rebuild_grid: null context%s%s");
     if (!c->scene_set) return fail(PAR_ERR_STATE, "par_rebuild_grid: no scene resident%s%s");
     DeviceGuard guard(c->cfg.device);
@@ -713,6 +725,7 @@ static int update_entities_impl(par_ctx* c, int first, int count, const par_aabb
 }
 
 int par_update_entities(par_ctx* c, int first, int count, const par_aabb* aabbs, const int32_t* sprite_ids) {
+    NvtxRange nvtx("par_update_entities");
     return update_entities_impl(c, first, count, aabbs, sprite_ids, nullptr, "par_update_entities");
 }
 
@@ -815,9 +828,14 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
             for (int t = first_owned, q = 0; q < (d.stripe_n == 1 ? 1 : n_owned); q++, t += d.stripe_n) {
                 const int sa = d.stripe_n == 1 ? ra : std::max(t * kBin, ra), sb = d.stripe_n == 1 ? rb : std::min((t + 1) * kBin, rb);
                 if (sb <= sa) continue;
-                PAR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(host_out) + (size_t)sa * pitch, pitch,
-                                           reinterpret_cast<const char*>(d_out) + (size_t)sa * row_bytes, row_bytes,
-                                           row_bytes, (size_t)(sb - sa), cudaMemcpyDeviceToHost, cs));
+                if (pitch == row_bytes)  // packed rows: a plain linear copy
+                    PAR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host_out) + (size_t)sa * pitch,
+                                             reinterpret_cast<const char*>(d_out) + (size_t)sa * row_bytes,
+                                             row_bytes * (size_t)(sb - sa), cudaMemcpyDeviceToHost, cs));
+                else
+                    PAR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(host_out) + (size_t)sa * pitch, pitch,
+                                               reinterpret_cast<const char*>(d_out) + (size_t)sa * row_bytes, row_bytes,
+                                               row_bytes, (size_t)(sb - sa), cudaMemcpyDeviceToHost, cs));
             }
         }
     }
@@ -843,6 +861,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
 }
 
 int par_render_device(par_ctx* c, const par_light* lights, int n_lights, void* d_rgba) {
+    NvtxRange nvtx("par_render_device");
     return render_impl(c, lights, n_lights, d_rgba ? static_cast<uchar4*>(d_rgba) : (c ? c->d_frame : nullptr),
                        nullptr);
 }
@@ -969,6 +988,7 @@ static int enqueue_resident_frame(par_ctx* c, const par_light* lights, int n_lig
 }
 
 int par_render_resident(par_ctx* c, const par_light* lights, int n_lights) {
+    NvtxRange nvtx("par_render_resident");
     if (!c || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
         return fail(PAR_ERR_INVALID_ARG, "par_render_resident: bad argument (at most 64 lights)%s%s");
     if (!c->scene_set) return fail(PAR_ERR_STATE, "par_render_resident: no scene resident%s%s");
@@ -1043,8 +1063,11 @@ int par_read_frame_pitched(par_ctx* c, void* dst, size_t pitch_bytes) {
     const size_t row_bytes = sizeof(par_color) * (size_t)c->d.W;
     if (pitch_bytes < row_bytes) return fail(PAR_ERR_INVALID_ARG, "par_read_frame_pitched: pitch smaller than a row%s%s");
     DeviceGuard guard(c->cfg.device);
-    PAR_CUDA(cudaMemcpy2DAsync(dst, pitch_bytes, c->d_frame, row_bytes, row_bytes, (size_t)c->d.H,
-                               cudaMemcpyDeviceToHost, c->stream));
+    if (pitch_bytes == row_bytes)
+        PAR_CUDA(cudaMemcpyAsync(dst, c->d_frame, row_bytes * (size_t)c->d.H, cudaMemcpyDeviceToHost, c->stream));
+    else
+        PAR_CUDA(cudaMemcpy2DAsync(dst, pitch_bytes, c->d_frame, row_bytes, row_bytes, (size_t)c->d.H,
+                                   cudaMemcpyDeviceToHost, c->stream));
     return PAR_OK;
 }
 
@@ -1066,9 +1089,13 @@ static int enqueue_owned_rows_d2h(par_ctx* c, const uchar4* d_src, par_color* ho
     const bool whole_tiles = first * kBin >= d.row0 && (last + 1) * kBin <= d.row1;
     char* dst = reinterpret_cast<char*>(host_frame);
     const char* src = reinterpret_cast<const char*>(d_src);
-    if (n == 1) {  // a band (or the whole frame): one block of rows
-        PAR_CUDA(cudaMemcpy2DAsync(dst + d.row0 * pitch, pitch, src + d.row0 * row_bytes, row_bytes, row_bytes,
-                                   (size_t)(d.row1 - d.row0), cudaMemcpyDeviceToHost, st));
+    if (n == 1) {  // a band (or the whole frame): one block of rows — a plain linear copy when the rows are packed
+        if (pitch == row_bytes)
+            PAR_CUDA(cudaMemcpyAsync(dst + d.row0 * pitch, src + d.row0 * row_bytes, row_bytes * (size_t)(d.row1 - d.row0),
+                                     cudaMemcpyDeviceToHost, st));
+        else
+            PAR_CUDA(cudaMemcpy2DAsync(dst + d.row0 * pitch, pitch, src + d.row0 * row_bytes, row_bytes, row_bytes,
+                                       (size_t)(d.row1 - d.row0), cudaMemcpyDeviceToHost, st));
         return PAR_OK;
     }
     if (whole_tiles && pitch == row_bytes) {  // the owned stripes lie at a regular pitch: one strided DMA
@@ -1193,15 +1220,18 @@ static int submit_impl(par_ctx* c, bool update, int first, const par_aabb* aabbs
 
 int par_submit_frame(par_ctx* c, const par_aabb* aabbs, const int32_t* sprite_ids, int n, const par_light* lights,
                      int n_lights, par_color* out_rgba) {
+    NvtxRange nvtx("par_submit_frame");
     return submit_impl(c, false, 0, aabbs, sprite_ids, n, lights, n_lights, out_rgba, "par_submit_frame");
 }
 
 int par_submit_update(par_ctx* c, int first, int count, const par_aabb* aabbs, const int32_t* sprite_ids,
                       const par_light* lights, int n_lights, par_color* out_rgba) {
+    NvtxRange nvtx("par_submit_update");
     return submit_impl(c, true, first, aabbs, sprite_ids, count, lights, n_lights, out_rgba, "par_submit_update");
 }
 
 int par_wait_frame(par_ctx* c, par_stats* stats) {
+    NvtxRange nvtx("par_wait_frame");
     if (!c) return fail(PAR_ERR_INVALID_ARG, "par_wait_frame: null context%s%s");
     if (c->slots_in_flight == 0) return fail(PAR_ERR_STATE, "par_wait_frame: no frame in flight%s%s");
     DeviceGuard guard(c->cfg.device);
@@ -1356,6 +1386,7 @@ int par_get_stats(par_ctx* c, par_stats* st) {
 
 int par_render(par_ctx* c, const par_light* lights, int n_lights, par_color* out_rgba,
                par_pixel* out_gbuf, par_stats* stats) {
+    NvtxRange nvtx("par_render");
     if (!c || !out_rgba) return fail(PAR_ERR_INVALID_ARG, "par_render: null argument%s%s");
     int rc = render_impl(c, lights, n_lights, c->d_frame, out_rgba, false, false, false, out_gbuf != nullptr);
     if (rc != PAR_OK) return rc;

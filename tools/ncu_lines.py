@@ -17,7 +17,7 @@ import subprocess
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO = os.path.join(ROOT, "pixel-art-raytracer_b200", "par_b200", "libpar_b200.so")
+SO = os.path.abspath(os.environ.get("PAR_B200_LIB") or os.path.join(ROOT, "pixel-art-raytracer_b200", "par_b200", "libpar_b200.so"))  # (override: A/B builds)
 
 
 def line_table(stem, kernel):
