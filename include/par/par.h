@@ -94,7 +94,8 @@ typedef struct par_config {
     int32_t stripe_index; /* t % stripe_count == stripe_index (interleaved stripes balance the   */
                           /* per-row cost over GPUs far better than contiguous bands); 0/1 = all */
     int32_t tile_order;   /* longest-tile-first CTA order from the previous frame's per-tile cost: */
-                          /* 0 = automatic (on for >= 2 lights), 1 = always, -1 = never            */
+                          /* 0 = automatic (>= 2 lights, or one light when the tiles make 1-3 waves */
+                          /* of resident CTAs), 1 = always, -1 = never                              */
     int32_t reserved[2];
 } par_config;
 

@@ -178,11 +178,17 @@ struct par_ctx {
     int* d_texel = nullptr;     // W*H ints, lazily allocated
     unsigned* d_tile_cost = nullptr;  // cycles per tile of the latest frame
     int* d_tile_order = nullptr;      // longest-first order computed from them
-    bool order_valid = false;
+    bool order_valid = false;   // d_tile_order holds an order of this context's tiles
+    bool cost_valid = false;    // d_tile_cost holds the costs of the latest ordered frame
+    bool order_fresh = false;   // ... and d_tile_order was computed from exactly those costs
+    bool order_forked = false;  // the order kernel is in flight on aux_stream: join before the render kernel
+    cudaStream_t aux_stream = nullptr;  // side branch of a frame: the tile-order kernel runs beside the scene loader
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     unsigned long long* d_phase_cycles = nullptr;  // debug only
     bool scene_set = false, frame_valid = false, build_timed = false, frame_timed = false;
     int launches_build = 0, launches_frame = 0, last_n_lights = 0;
     float ambient = 0.25f;
+    int cta_slots = 0;     // render-kernel CTAs the device holds at a time (SMs x CTAs per SM)
     size_t out_pitch = 0;  // row pitch of host frames (0 = packed)
     // fused multi-GPU frame exchange: raster frames of the other ranks, mapped into this process
     uchar4* peer_frame[8] = {};
@@ -373,6 +379,9 @@ int par_create(par_ctx** out, const par_config* cfg) {
         PAR_CUDA(cudaEventCreate(&c->ev_build0));
         PAR_CUDA(cudaEventCreate(&c->ev_build1));
         PAR_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        PAR_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        PAR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        PAR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
         PAR_CUDA(cudaEventCreate(&c->ev_f0));
         PAR_CUDA(cudaEventCreate(&c->ev_f2));
         PAR_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
@@ -411,6 +420,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
         c->d_footer = reinterpret_cast<ExchangeFooter*>(c->d_frame_block + c->footer_offset);
         PAR_CUDA(cudaMemsetAsync(c->d_frame_block, 0, c->footer_offset + 256, c->stream));
         PAR_CUDA(configure_tile());
+        c->cta_slots = prop.multiProcessorCount * tile_ctas_per_sm();
         return PAR_OK;
     }();
     if (rc != PAR_OK) {
@@ -427,6 +437,7 @@ void par_destroy(par_ctx* c) {
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     if (c->stream && c->stream != c->own_stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     cudaFree(c->d_raw);
     cudaFree(c->d_sprite_ids);
     for (GridBuffers& g : c->gen) {
@@ -465,6 +476,9 @@ void par_destroy(par_ctx* c) {
     for (auto& ev : c->ev_chunk)
         for (cudaEvent_t e : ev)
             if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -756,7 +770,37 @@ static void fill_tile_params(par_ctx* c, TileParams& tp, const par_light* lights
 static bool want_tile_order(const par_ctx* c, int n_lights) {
     if (c->debug_flags & 32) return false;
     if (c->debug_flags & 64) return true;
-    return c->cfg.tile_order > 0 || (c->cfg.tile_order == 0 && n_lights >= 2);
+    if (c->cfg.tile_order != 0) return c->cfg.tile_order > 0;
+    if (n_lights >= 2) return true;  // tile costs differ by an order of magnitude: always worth it
+    // One light: costs vary mildly, so the order only pays through the tail of the last wave — when the owned tiles
+    // make between one and three waves of resident CTAs (measured: -10 % at 1920x1080 = 1.75 waves, nothing at
+    // 3840x2160 = 7 waves, a launch too many at 480x320 = 0.13 waves).
+    int first, rows;
+    owned_tile_rows(c->d, first, rows);
+    const long tiles = (long)rows * c->d.HW;
+    return n_lights == 1 && tiles >= c->cta_slots && tiles <= 3L * c->cta_slots;
+}
+
+// Longest-tile-first order for the NEXT render kernel from the costs the previous one recorded.  The sort
+// (one small block) runs on a side branch beside the scene loader, so it never sits on a frame's critical
+// path; inside a graph capture the branch becomes a parallel node.  join_tile_order makes the main stream
+// wait for it (render_impl does, right before the render kernel).
+static int fork_tile_order(par_ctx* c, int n_lights) {
+    if (!want_tile_order(c, n_lights) || !c->cost_valid || c->order_fresh || c->order_forked) return PAR_OK;
+    PAR_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+    PAR_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    PAR_CUDA(launch_tile_order(c->d_tile_cost, c->d_tile_order, c->d, c->aux_stream));
+    PAR_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+    c->order_forked = true;
+    return PAR_OK;
+}
+
+static int join_tile_order(par_ctx* c) {
+    if (!c->order_forked) return PAR_OK;
+    PAR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+    c->order_forked = false;
+    c->order_valid = c->order_fresh = true;
+    return PAR_OK;
 }
 
 // Launch the render kernel for the context's band into d_out.  With host_out the band is cut
@@ -807,6 +851,18 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     }
     const bool ordered = n_chunks == 1 && want_tile_order(c, n_lights);
     int extra_launches = 0;
+    {   // the CTA order of this frame: forked beside the loader by the frame-level calls, else computed here
+        const bool was_forked = c->order_forked;
+        int rc = join_tile_order(c);
+        if (rc != PAR_OK) return rc;
+        if (ordered && c->cost_valid && !c->order_fresh) {
+            PAR_CUDA(launch_tile_order(c->d_tile_cost, c->d_tile_order, d, c->stream));
+            c->order_valid = c->order_fresh = true;
+            extra_launches = 1;
+        } else if (was_forked) {
+            extra_launches = 1;
+        }
+    }
     PAR_CUDA(record_timing(c, c->ev_f0));
     for (int k = 0; k < n_chunks; k++) {
         const int ta = tile0 + (tile1 - tile0) * k / n_chunks, tb = tile0 + (tile1 - tile0) * (k + 1) / n_chunks;
@@ -840,12 +896,11 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
         }
     }
     PAR_CUDA(record_timing(c, c->ev_f2));
-    if (ordered) {  // next frame's CTA order from this frame's tile costs (off the frame's critical path)
-        PAR_CUDA(launch_tile_order(c->d_tile_cost, c->d_tile_order, d, c->stream));
-        c->order_valid = true;
-        extra_launches = 1;
+    if (ordered) {  // this frame recorded its tile costs: the next frame sorts its CTAs by them
+        c->cost_valid = true;
+        c->order_fresh = false;
     } else {
-        c->order_valid = false;
+        c->cost_valid = c->order_valid = c->order_fresh = false;
     }
     if (host_out && n_chunks > 1) {  // make the context's stream cover the copies too
         PAR_CUDA(cudaEventRecord(c->ev_copy, c->copy_stream));
@@ -973,8 +1028,9 @@ static int enqueue_resident_frame(par_ctx* c, const par_light* lights, int n_lig
         // starting frame k releases frame k - 1: producers may overwrite my frame again
         if (their_credit.n) k_flag_signal<<<1, 32, 0, c->stream>>>(their_credit, c->d_seq + 1, 1u);
     }
-    int rc = run_loader(c);
+    int rc = fork_tile_order(c, n_lights);  // beside the loader
     if (rc != PAR_OK) return rc;
+    if ((rc = run_loader(c)) != PAR_OK) return rc;
     // frame k (= produced + 1) may be stored once every consumer has released frame k - 1
     if (ex && mine_credit.n) k_flag_wait<<<1, 32, 0, c->stream>>>(mine_credit, c->d_seq + 0, 0u, 0, c->h_exchange_timeout);
     if ((rc = render_impl(c, lights, n_lights, c->d_frame, nullptr, false, ex)) != PAR_OK) return rc;
@@ -1007,8 +1063,12 @@ int par_render_resident(par_ctx* c, const par_light* lights, int n_lights) {
     }
     const int parity = c->cur;  // the graph for "current generation = parity" builds into parity ^ 1
     const bool ordered = want_tile_order(c, n_lights);
-    if (c->resident_ok[parity] && c->resident_epoch[parity] == c->epoch && (!ordered || c->order_valid)) {
+    if (c->resident_ok[parity] && c->resident_epoch[parity] == c->epoch && (!ordered || c->cost_valid)) {
         PAR_CUDA(cudaGraphLaunch(c->resident_exec[parity], c->stream));
+        if (ordered) {  // what the captured calls do to the order state
+            c->order_valid = true;
+            c->order_fresh = false;
+        }
         // host-side state the captured calls would have updated
         const int nxt = c->cur ^ 1;
         c->gen_dirty[c->cur] = false;
@@ -1023,7 +1083,7 @@ int par_render_resident(par_ctx* c, const par_light* lights, int n_lights) {
         return PAR_OK;
     }
     // the first ordered frame has no costs yet: its graph would bake "no order" in, so run it plainly
-    if (ordered && !c->order_valid) return enqueue_resident_frame(c, lights, n_lights);
+    if (ordered && !c->cost_valid) return enqueue_resident_frame(c, lights, n_lights);
     PAR_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     c->capturing = true;
     int rc = enqueue_resident_frame(c, lights, n_lights);
@@ -1033,6 +1093,7 @@ int par_render_resident(par_ctx* c, const par_light* lights, int n_lights) {
     if (rc != PAR_OK) {
         if (graph) cudaGraphDestroy(graph);
         cudaGetLastError();
+        c->order_forked = false;  // (a side branch of the abandoned capture is gone with it)
         return rc;
     }
     PAR_CUDA(ce);
@@ -1164,7 +1225,9 @@ static int submit_impl(par_ctx* c, bool update, int first, const par_aabb* aabbs
     }
     LoaderCounters* slot_ctr = &c->h_ctr[1 + slot];
     auto enqueue = [&]() -> int {
-        int rc = update ? update_entities_impl(c, first, n, aabbs, sprite_ids, slot_ctr, who)
+        int rc = fork_tile_order(c, n_lights);  // beside the upload and the loader
+        if (rc == PAR_OK)
+            rc = update ? update_entities_impl(c, first, n, aabbs, sprite_ids, slot_ctr, who)
                         : set_scene_impl(c, aabbs, sprite_ids, n, slot_ctr);
         if (rc == PAR_OK) rc = render_impl(c, lights, n_lights, d_out, nullptr, false, false, true);
         return rc;
@@ -1185,6 +1248,7 @@ static int submit_impl(par_ctx* c, bool update, int first, const par_aabb* aabbs
         if (rc != PAR_OK) {
             if (graph) cudaGraphDestroy(graph);
             cudaGetLastError();
+            c->order_forked = false;  // (a side branch of the abandoned capture is gone with it)
             return rc;
         }
         PAR_CUDA(ce);

@@ -101,6 +101,7 @@ struct TileParams {
 };
 size_t tile_smem_bytes();
 cudaError_t configure_tile();  // per device, before the first launch
+int tile_ctas_per_sm();        // resident CTAs of the production kernel per SM (after configure_tile)
 cudaError_t launch_tile(const TileParams& p, cudaStream_t s);
 cudaError_t launch_tile_order(const unsigned* cost, int* order, const ViewDims& d, cudaStream_t s);
 

@@ -1009,6 +1009,16 @@ cudaError_t configure_tile() {
     return cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
 }
 
+// CTAs of the production render kernel one SM holds at a time (occupancy query; 5 on sm_100).
+int tile_ctas_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<false>, kT, sizeof(TileSmem)) != cudaSuccess) {
+        cudaGetLastError();
+        n = PAR_TILE_MIN_CTAS;
+    }
+    return n > 0 ? n : 1;
+}
+
 cudaError_t launch_tile(const TileParams& p, cudaStream_t st) {
     int first, tile_rows;
     owned_tile_rows(p.d, first, tile_rows);
