@@ -248,8 +248,11 @@ int par_set_output_pitch(par_ctx* ctx, size_t pitch_bytes);
 int par_read_frame_pitched(par_ctx* ctx, void* dst, size_t pitch_bytes);
 
 /* Render a frame from the RESIDENT scene: device scene loader + render kernel, asynchronously on
- * the context's stream, into the context's own frame (par_device_frame).  The launch sequence is
- * captured once into CUDA graphs and replayed while the lights stay the same.  With an exchange
+ * the context's stream, into the context's own frame (par_device_frame).  The current grid generation
+ * is always the grid of the resident scene (every scene call rebuilds or patches it at once), so the
+ * frame renders from it while the loader — the reference re-bins every frame, alternative.cpp:689-693 —
+ * rebuilds the OTHER generation from the same scene on a side branch, for the next frame.  The launch
+ * sequence is captured once into CUDA graphs and replayed while the lights stay the same.  With an exchange
  * set up (par_exchange_setup) the call also carries the multi-GPU frame exchange: the render
  * kernel's stores go to the consumers' frames as well, arrival is signalled through flags in the
  * consumers' frame footers, consumers wait for all producers on their stream, and a producer does

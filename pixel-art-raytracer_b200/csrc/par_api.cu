@@ -183,7 +183,13 @@ struct par_ctx {
     bool order_fresh = false;   // ... and d_tile_order was computed from exactly those costs
     bool order_forked = false;  // the order kernel is in flight on aux_stream: join before the render kernel
     cudaStream_t aux_stream = nullptr;  // side branch of a frame: the tile-order kernel runs beside the scene loader
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_side = nullptr;
+    // par_render_resident, overlapped form: the frame of grid generation p renders while generation p ^ 1 is rebuilt
+    // on the side branch.  Tile costs / orders are kept per generation parity (a frame's order comes from the costs of
+    // the previous frame of the same parity, sorted during the frame in between).
+    unsigned* d_res_cost[2] = {};
+    int* d_res_order[2] = {};
+    bool res_cost_valid[2] = {false, false}, res_order_valid[2] = {false, false};
     unsigned long long* d_phase_cycles = nullptr;  // debug only
     bool scene_set = false, frame_valid = false, build_timed = false, frame_timed = false;
     int launches_build = 0, launches_frame = 0, last_n_lights = 0;
@@ -265,6 +271,12 @@ int run_loader(par_ctx* c, LoaderCounters* slot_ctr = nullptr) {
     lp.host_a = c->h_ctr;
     lp.host_b = slot_ctr;
     PAR_CUDA(record_timing(c, c->ev_build0));
+    if (c->gen_dirty[nxt]) {  // left behind by an overlapped resident frame: the target generation is cleared on its own first
+        PAR_CUDA(launch_clear_touched(c->d, c->gen[nxt], c->capturing ? c->cap_entities : c->list_bound[nxt], c->stream,
+                                      &c->launches_build));
+        c->gen_dirty[nxt] = false;
+        c->list_bound[nxt] = 0;
+    }
     PAR_CUDA(launch_scene_loader(lp, c->stream, &c->launches_build));
     PAR_CUDA(record_timing(c, c->ev_build1));
     c->gen_dirty[c->cur] = false;  // cleared by this launch (its counters are re-armed by k_occupancy)
@@ -382,6 +394,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
         PAR_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
         PAR_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         PAR_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+        PAR_CUDA(cudaEventCreateWithFlags(&c->ev_side, cudaEventDisableTiming));
         PAR_CUDA(cudaEventCreate(&c->ev_f0));
         PAR_CUDA(cudaEventCreate(&c->ev_f2));
         PAR_CUDA(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
@@ -408,6 +421,11 @@ int par_create(par_ctx** out, const par_config* cfg) {
         PAR_CUDA(cudaMalloc(&c->d_tile_cost, sizeof(unsigned) * tiles));
         PAR_CUDA(cudaMalloc(&c->d_tile_order, sizeof(int) * tiles));
         PAR_CUDA(cudaMemsetAsync(c->d_tile_cost, 0, sizeof(unsigned) * tiles, c->stream));
+        for (int k = 0; k < 2; k++) {
+            PAR_CUDA(cudaMalloc(&c->d_res_cost[k], sizeof(unsigned) * tiles));
+            PAR_CUDA(cudaMalloc(&c->d_res_order[k], sizeof(int) * tiles));
+            PAR_CUDA(cudaMemsetAsync(c->d_res_cost[k], 0, sizeof(unsigned) * tiles, c->stream));
+        }
         PAR_CUDA(cudaMalloc(&c->d_seq, 4 * sizeof(unsigned)));
         PAR_CUDA(cudaMemsetAsync(c->d_seq, 0, 4 * sizeof(unsigned), c->stream));
         PAR_CUDA(cudaMallocHost(&c->h_exchange_timeout, sizeof(int)));
@@ -455,6 +473,10 @@ void par_destroy(par_ctx* c) {
         if (c->peer_frame[r] && c->peer_is_ipc[r]) cudaIpcCloseMemHandle(c->peer_frame[r]);
     cudaFree(c->d_tile_cost);
     cudaFree(c->d_tile_order);
+    for (int k = 0; k < 2; k++) {
+        cudaFree(c->d_res_cost[k]);
+        cudaFree(c->d_res_order[k]);
+    }
     cudaFree(c->d_seq);
     cudaFree(c->d_gbuf);
     cudaFree(c->d_frame_block);
@@ -478,6 +500,7 @@ void par_destroy(par_ctx* c) {
             if (e) cudaEventDestroy(e);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_side) cudaEventDestroy(c->ev_side);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -807,8 +830,14 @@ static int join_tile_order(par_ctx* c) {
 // into up to kMaxChunks row chunks (whole tile rows) and the D2H copy of chunk k overlaps the
 // rendering of chunk k+1 on a second stream — at 4K the 33 MB readback takes longer than the
 // kernel, so the drop-in call is roughly max(render, copy) instead of their sum.
+struct TileOrderIO {   // explicit tile cost / order buffers of a frame (the overlapped resident frame), instead of the
+    unsigned* cost;    // context's generic ones
+    const int* order;
+};
+
 static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4* d_out, par_color* host_out,
-                       bool striped_out = false, bool to_peers = false, bool pipelined = false, bool want_gbuf = false) {
+                       bool striped_out = false, bool to_peers = false, bool pipelined = false, bool want_gbuf = false,
+                       const TileOrderIO* io = nullptr) {
     if (c && c->slots_in_flight && !pipelined)
         return fail(PAR_ERR_STATE, "par_render: pipelined frames in flight, call par_wait_frame first%s%s");
     if (!c || n_lights < 0 || n_lights > PAR_MAX_LIGHTS || (n_lights > 0 && !lights))
@@ -849,7 +878,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
         const float copy_ms = (float)(d.row1 - d.row0) * d.W * 4.f / 50e6f;  // ~50 GB/s PCIe gen5
         if (pinned && c->last_kernel_ms > 0.f && c->last_kernel_ms < 2.5f * copy_ms) n_chunks = c->readback_chunks;
     }
-    const bool ordered = n_chunks == 1 && want_tile_order(c, n_lights);
+    const bool ordered = !io && n_chunks == 1 && want_tile_order(c, n_lights);
     int extra_launches = 0;
     {   // the CTA order of this frame: forked beside the loader by the frame-level calls, else computed here
         const bool was_forked = c->order_forked;
@@ -872,8 +901,8 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
         int first_owned, n_owned;
         owned_tile_rows(tp.d, first_owned, n_owned);
         tp.tile_row_first = first_owned;
-        tp.tile_cost = ordered ? c->d_tile_cost : nullptr;
-        tp.tile_order = ordered && c->order_valid ? c->d_tile_order : nullptr;
+        tp.tile_cost = io ? io->cost : ordered ? c->d_tile_cost : nullptr;
+        tp.tile_order = io ? io->order : ordered && c->order_valid ? c->d_tile_order : nullptr;
         PAR_CUDA(record_timing(c, c->ev_chunk[k][0]));
         PAR_CUDA(launch_tile(tp, c->stream));
         PAR_CUDA(record_timing(c, c->ev_chunk[k][1]));
@@ -899,7 +928,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
     if (ordered) {  // this frame recorded its tile costs: the next frame sorts its CTAs by them
         c->cost_valid = true;
         c->order_fresh = false;
-    } else {
+    } else if (!io) {
         c->cost_valid = c->order_valid = c->order_fresh = false;
     }
     if (host_out && n_chunks > 1) {  // make the context's stream cover the copies too
@@ -1007,7 +1036,40 @@ static ExchangeFooter* footer_of(par_ctx* c, int r) {
 // One frame from the resident scene on c->stream: [credit: release the previous frame] -> loader ->
 // [wait for the consumers' credits] -> render kernel (+ peer stores) -> [signal arrival] ->
 // [consumers: wait for all arrivals].
-static int enqueue_resident_frame(par_ctx* c, const par_light* lights, int n_lights) {
+// Overlapped form (overlap == true): the frame renders from the current grid generation p — always the grid of the
+// resident scene: every scene change rebuilds or patches it at once — while the side branch clears and rebuilds
+// generation p ^ 1 from the same scene for the next frame (and sorts the next frame's tile order).  Every frame
+// still runs one scene loader and one render kernel; the loader just no longer sits in front of the kernel.
+static int enqueue_resident_frame(par_ctx* c, const par_light* lights, int n_lights, bool overlap) {
+    const int gp = c->cur, gq = c->cur ^ 1;
+    const bool ordered = overlap && want_tile_order(c, n_lights);
+    int side_launches = 0;
+    if (overlap) {
+        PAR_CUDA(cudaEventRecord(c->ev_fork, c->stream));
+        PAR_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        if (ordered && c->res_cost_valid[gq]) {  // the next frame's CTA order, from the costs of the previous frame of its parity
+            PAR_CUDA(launch_tile_order(c->d_res_cost[gq], c->d_res_order[gq], c->d, c->aux_stream));
+            c->res_order_valid[gq] = true;
+            side_launches++;
+        }
+        if (c->capturing || c->gen_dirty[gq])
+            PAR_CUDA(launch_clear_touched(c->d, c->gen[gq], c->capturing ? c->cap_entities : c->list_bound[gq], c->aux_stream,
+                                          &side_launches));
+        LoaderParams lp;
+        lp.d = c->d;
+        lp.raw = c->d_raw;
+        lp.sprite_ids = c->has_sprite_ids ? c->d_sprite_ids : nullptr;
+        lp.sprite_dims = c->d_sprite_dims;
+        lp.n = c->n_entities;
+        lp.n_sprites = c->n_sprites;
+        lp.cur = c->gen[gq];
+        lp.old = GridBuffers{};  // nothing to clear in the same launch
+        lp.old_n_list_cap = 0;
+        lp.host_a = c->h_ctr;
+        lp.host_b = nullptr;
+        PAR_CUDA(launch_scene_loader(lp, c->aux_stream, &side_launches));
+        PAR_CUDA(cudaEventRecord(c->ev_side, c->aux_stream));
+    }
     const int me = c->d.stripe_i, n = c->d.stripe_n;
     const bool ex = c->exchange_on;
     const bool consumer = ex && (c->exchange_root < 0 || c->exchange_root == me);
@@ -1028,17 +1090,31 @@ static int enqueue_resident_frame(par_ctx* c, const par_light* lights, int n_lig
         // starting frame k releases frame k - 1: producers may overwrite my frame again
         if (their_credit.n) k_flag_signal<<<1, 32, 0, c->stream>>>(their_credit, c->d_seq + 1, 1u);
     }
-    int rc = fork_tile_order(c, n_lights);  // beside the loader
-    if (rc != PAR_OK) return rc;
-    if ((rc = run_loader(c)) != PAR_OK) return rc;
+    int rc = PAR_OK;
+    if (!overlap) {
+        if ((rc = fork_tile_order(c, n_lights)) != PAR_OK) return rc;  // beside the loader
+        if ((rc = run_loader(c)) != PAR_OK) return rc;
+    }
     // frame k (= produced + 1) may be stored once every consumer has released frame k - 1
     if (ex && mine_credit.n) k_flag_wait<<<1, 32, 0, c->stream>>>(mine_credit, c->d_seq + 0, 0u, 0, c->h_exchange_timeout);
-    if ((rc = render_impl(c, lights, n_lights, c->d_frame, nullptr, false, ex)) != PAR_OK) return rc;
+    const TileOrderIO io{ordered ? c->d_res_cost[gp] : nullptr, ordered && c->res_order_valid[gp] ? c->d_res_order[gp] : nullptr};
+    if ((rc = render_impl(c, lights, n_lights, c->d_frame, nullptr, false, ex, false, false, overlap ? &io : nullptr)) != PAR_OK)
+        return rc;
     if (ex) {
         if (their_arrive.n) k_flag_signal<<<1, 32, 0, c->stream>>>(their_arrive, c->d_seq + 0, 0u);
         if (mine_arrive.n) k_flag_wait<<<1, 32, 0, c->stream>>>(mine_arrive, c->d_seq + 2, 1u, 1, c->h_exchange_timeout);
         PAR_CUDA(cudaGetLastError());
         c->launches_frame += (their_credit.n > 0) + (mine_credit.n > 0) + (their_arrive.n > 0) + (mine_arrive.n > 0);
+    }
+    if (overlap) {  // join the side branch; the rebuilt generation becomes the current one
+        PAR_CUDA(cudaStreamWaitEvent(c->stream, c->ev_side, 0));
+        c->res_cost_valid[gp] = ordered;
+        c->gen_dirty[gq] = true;  // (gen[gp] stays dirty: it is cleared when it is the side branch's target, next frame)
+        c->list_bound[gq] = c->n_entities;
+        c->cur = gq;
+        c->launches_build = side_launches;
+        c->build_timed = false;
+        c->gbuf_valid = false;
     }
     return PAR_OK;
 }
@@ -1052,7 +1128,11 @@ int par_render_resident(par_ctx* c, const par_light* lights, int n_lights) {
     DeviceGuard guard(c->cfg.device);
     const bool graph_ok = !(c->debug_flags & 16) && c->stream != nullptr && c->stream != cudaStreamLegacy &&
                           c->stream != cudaStreamPerThread && !c->d_phase_cycles;
-    if (!graph_ok) return enqueue_resident_frame(c, lights, n_lights);
+    // Overlapped form (default): the scene loader rebuilds the other grid generation on a side branch while this
+    // frame renders.  PAR_DEBUG_FLAGS & 128 (and streams that cannot fork) keep the loader in front of the kernel.
+    const bool overlap = !(c->debug_flags & 128) && c->stream != nullptr && c->stream != cudaStreamLegacy &&
+                         c->stream != cudaStreamPerThread;
+    if (!graph_ok) return enqueue_resident_frame(c, lights, n_lights, overlap);
     // cached graphs are valid for one (lights, configuration) key and one grid generation each
     const bool same_key = c->resident_n_lights == n_lights &&
                           (n_lights == 0 || memcmp(c->resident_lights, lights, sizeof(par_light) * (size_t)n_lights) == 0);
@@ -1062,18 +1142,24 @@ int par_render_resident(par_ctx* c, const par_light* lights, int n_lights) {
         if (n_lights) memcpy(c->resident_lights, lights, sizeof(par_light) * (size_t)n_lights);
     }
     const int parity = c->cur;  // the graph for "current generation = parity" builds into parity ^ 1
+    const int nxt = parity ^ 1;
     const bool ordered = want_tile_order(c, n_lights);
-    if (c->resident_ok[parity] && c->resident_epoch[parity] == c->epoch && (!ordered || c->cost_valid)) {
+    // A graph bakes in whether the frame uses a tile order and whether one is being sorted: capture only in the steady state.
+    const bool steady = !ordered || (overlap ? c->res_order_valid[parity] && c->res_cost_valid[nxt] : c->cost_valid);
+    if (c->resident_ok[parity] && c->resident_epoch[parity] == c->epoch && steady) {
         PAR_CUDA(cudaGraphLaunch(c->resident_exec[parity], c->stream));
-        if (ordered) {  // what the captured calls do to the order state
-            c->order_valid = true;
-            c->order_fresh = false;
-        }
         // host-side state the captured calls would have updated
-        const int nxt = c->cur ^ 1;
-        c->gen_dirty[c->cur] = false;
-        c->list_bound[c->cur] = 0;
-        c->gen_dirty[nxt] = true;
+        if (overlap) {
+            c->gen_dirty[nxt] = true;  // (the generation rendered from stays dirty until it is the side branch's target)
+        } else {
+            if (ordered) {
+                c->order_valid = true;
+                c->order_fresh = false;
+            }
+            c->gen_dirty[parity] = false;
+            c->list_bound[parity] = 0;
+            c->gen_dirty[nxt] = true;
+        }
         c->list_bound[nxt] = c->n_entities;
         c->cur = nxt;
         c->frame_valid = true;
@@ -1082,11 +1168,11 @@ int par_render_resident(par_ctx* c, const par_light* lights, int n_lights) {
         c->last_n_lights = n_lights;
         return PAR_OK;
     }
-    // the first ordered frame has no costs yet: its graph would bake "no order" in, so run it plainly
-    if (ordered && !c->cost_valid) return enqueue_resident_frame(c, lights, n_lights);
+    // the first ordered frames have no costs / order yet: their graph would bake "no order" in, so run them plainly
+    if (!steady) return enqueue_resident_frame(c, lights, n_lights, overlap);
     PAR_CUDA(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     c->capturing = true;
-    int rc = enqueue_resident_frame(c, lights, n_lights);
+    int rc = enqueue_resident_frame(c, lights, n_lights, overlap);
     c->capturing = false;
     cudaGraph_t graph = nullptr;
     cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);

@@ -40,6 +40,9 @@ struct LoaderParams {
     LoaderCounters* host_b;
 };
 cudaError_t launch_scene_loader(const LoaderParams& p, cudaStream_t s, int* launches);
+// Clear the bins a generation's last build touched and re-arm its counters (n_list_cap: host-side upper bound
+// of its survivor list).
+cudaError_t launch_clear_touched(const ViewDims& d, const GridBuffers& g, int n_list_cap, cudaStream_t s, int* launches);
 // Whole-grid clear (context creation / recovery): insert totals 0, slots -1, occupancy 0, counters 0.
 cudaError_t launch_clear_grid(const GridBuffers& g, int V, cudaStream_t s);
 

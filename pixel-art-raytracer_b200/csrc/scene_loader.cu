@@ -16,6 +16,7 @@
 //                   survivor list touched (C2: 32 k of 280 k bins, C5: 42 k of 2.2 M), instead of a
 //                   memset of the whole grid.  Two generations alternate, so the clear of the grid
 //                   frame k-1 used never sits between frame k's kernels.
+//   (k_clear_touched + k_reset_counters clear a generation on its own, for the pipelined resident frame.)
 //   k_occupancy     one thread per survivor: write each spanned bin's wrapped count into a 4-bit-
 //                   per-bin table (read by the shadow walk: one small load answers "occupied?" and
 //                   "how many?"); the last block to finish publishes the counters straight into
@@ -65,23 +66,26 @@ __device__ __forceinline__ void clear_bin(const GridBuffers& g, int f) {
 
 }  // namespace
 
+// Clear the bins listed survivor t of generation g touched in its last build.
+__device__ __forceinline__ void clear_touched(const ViewDims& d, const GridBuffers& g, int t) {
+    const Box b = unpack_box(g.boxes[g.survivors[t]]);
+    BinRange r;
+    if (cull_and_range(d, b, r))
+        for (int x = r.x0; x < r.x1; x++)
+            for (int y = r.y0; y < r.y1; y++)
+                for (int z = r.z0; z < r.z1; z++) {
+                    const int f = flat_bin(d, x, y, z);
+                    clear_bin(g, f);
+                    g.occ4[f >> 3] = 0u;  // every non-zero nibble belongs to a touched bin: all end up 0
+                }
+}
+
 __global__ void __launch_bounds__(256)
 k_load_insert(const __grid_constant__ LoaderParams p) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     const ViewDims& d = p.d;
     // (b) clear what the other generation's last build touched
-    if (p.old.cnt && t < p.old.ctr->n_list) {
-        const Box b = unpack_box(p.old.boxes[p.old.survivors[t]]);
-        BinRange g;
-        if (cull_and_range(d, b, g))
-            for (int x = g.x0; x < g.x1; x++)
-                for (int y = g.y0; y < g.y1; y++)
-                    for (int z = g.z0; z < g.z1; z++) {
-                        const int f = flat_bin(d, x, y, z);
-                        clear_bin(p.old, f);
-                        p.old.occ4[f >> 3] = 0u;  // every non-zero nibble belongs to a touched bin: all end up 0
-                    }
-    }
+    if (p.old.cnt && t < p.old.ctr->n_list) clear_touched(d, p.old, t);
     // (a) this frame's entity
     if (t >= p.n) return;
     int4 r = p.raw[t];
@@ -155,6 +159,24 @@ k_clear_grid(GridBuffers g, int V) {
     for (size_t i = tid; i < (size_t)V; i += nthr) g.cnt[i] = 0;
     for (size_t i = tid; i < ((size_t)V + 7) / 8; i += nthr) g.occ4[i] = 0u;
     if (tid == 0) *g.ctr = LoaderCounters{0, 0, INT_MAX, 0, 0, 0, {0, 0}};
+}
+
+// A generation cleared on its own (the pipelined resident frame rebuilds the generation the previous frame
+// rendered from while the current frame renders from the other one): the touched bins first, then — a second
+// launch, because the list length lives in the counters — the counters.
+__global__ void __launch_bounds__(256)
+k_clear_touched(ViewDims d, GridBuffers g) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < g.ctr->n_list) clear_touched(d, g, t);
+}
+
+__global__ void k_reset_counters(LoaderCounters* ctr) { *ctr = LoaderCounters{0, 0, INT_MAX, 0, 0, 0, {0, 0}}; }
+
+cudaError_t launch_clear_touched(const ViewDims& d, const GridBuffers& g, int n_list_cap, cudaStream_t s, int* launches) {
+    k_clear_touched<<<std::max(1, (n_list_cap + 255) / 256), 256, 0, s>>>(d, g);
+    k_reset_counters<<<1, 1, 0, s>>>(g.ctr);
+    *launches += 2;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_clear_grid(const GridBuffers& g, int V, cudaStream_t s) {

@@ -1046,6 +1046,72 @@ def test_resident_frames_graph_replay(par, tile_order):
         assert r.stats()["n_survivors"] > 0
 
 
+@pytest.mark.parametrize("flags", ["0", "128"])
+def test_resident_frames_interleaved_with_scene_calls(par, oracle, monkeypatch, flags):
+    """The overlapped resident frame renders from one grid generation while the other is rebuilt beside it
+    (PAR_DEBUG_FLAGS=128: loader in front of the kernel instead).  Whatever comes in between — incremental
+    updates, a new scene, a rebuild, blocking renders, pipelined frames, the parity checkpoints — every
+    frame and every grid read back equals the oracle's for the scene resident at that moment."""
+    monkeypatch.setenv("PAR_DEBUG_FLAGS", flags)
+    W, H, L = 960, 680, 680
+    boxes, lights = par.scene_synthetic(W, H, L, n=4000, n_lights=3)
+    boxes = boxes.copy()
+    rng = np.random.default_rng(7)
+
+    def check(r, tag, resident_frames):
+        ref = oracle.render(W, H, L, np.ascontiguousarray(boxes, oracle.AABB), lights.view(oracle.LIGHT))
+        for k in range(resident_frames):
+            r.render_resident(lights)
+        got = r.read_frame()
+        r.sync()
+        assert np.array_equal(_u32(got), _u32(ref["rgba"])), f"{tag}: resident frame"
+        count, ids = r.grid()
+        ocount, _, oent = oracle.grid_build(W, H, L, np.ascontiguousarray(boxes, oracle.AABB))
+        assert np.array_equal(count, ocount), f"{tag}: grid counts"
+        oent = oent.reshape(-1, 8)
+        live = np.arange(8)[None, :] < ocount[:, None]
+        assert np.array_equal(np.where(live, ids, -1), np.where(live, oent, -1)), f"{tag}: grid entity map"
+        gbuf, _ = r.gbuffer()
+        assert gbuf.tobytes() == ref["gbuf"].tobytes(), f"{tag}: G-buffer"
+        return ref
+
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        check(r, "fresh scene", 1)
+        check(r, "replays", 5)
+        for step in range(3):  # incremental updates between resident frames (odd and even numbers of frames)
+            boxes["px"][:3] += rng.integers(-30, 30, 3).astype(np.int16)
+            boxes["pz"][:3] += rng.integers(-30, 30, 3).astype(np.int16)
+            r.update_entities(0, boxes[:3])
+            check(r, f"update {step}", 1 + step)
+        boxes[100:2000] = boxes[2000:3900]  # a different scene of the same size
+        r.set_scene(boxes)
+        check(r, "new scene", 2)
+        r.rebuild_grid()
+        ref = check(r, "after rebuild", 3)
+        rgba, _ = r.render(lights)  # blocking render from the grid the resident frames left behind
+        assert np.array_equal(_u32(rgba), _u32(ref["rgba"]))
+        check(r, "after blocking render", 1)
+        h_boxes = par.pinned_empty(len(boxes), par.AABB)
+        boxes["py"][:200] += 15
+        h_boxes[:] = boxes
+        out = par.pinned_empty((H, W), par.COLOR)
+        r.submit_frame(h_boxes, lights, out)  # pipelined frame with a full upload
+        r.wait_frame()
+        ref = check(r, "after a pipelined frame", 2)
+        assert np.array_equal(_u32(out), _u32(ref["rgba"]))
+        boxes["px"][0] += 25
+        r.submit_update(0, boxes[:1], lights, out)  # pipelined frame with an incremental update
+        r.wait_frame()
+        ref = check(r, "after a pipelined update", 3)
+        assert np.array_equal(_u32(out), _u32(ref["rgba"]))
+        small = boxes[:1500].copy()  # a smaller scene: the survivor lists of both generations shrink
+        boxes = small
+        r.set_scene(boxes)
+        check(r, "smaller scene", 4)
+
+
 def test_two_contexts_share_a_device(par, oracle):
     """Contexts with different views and atlases on one device do not disturb each other."""
     rng = np.random.default_rng(5)

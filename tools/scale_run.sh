@@ -24,7 +24,7 @@ for r in rows:
     k = r["kernels_ms"]
     base.setdefault("c2", r["ms_per_step"] * n)
     print(f"N={n}  C2 {r['ms_per_step']:.4f} ms/step  x{base['c2'] / r['ms_per_step'] / 1:.2f} eff {base['c2'] / r['ms_per_step'] / n * (1 if rows[0]['n_gpus'] == 1 else 1):.2f}  "
-          f"loader {k['scene_loader']} k_tile {k['k_tile_min']}..{k['k_tile_max']} gap {k['step_minus_kernels_ms']}  "
+          f"loader {k['scene_loader']} k_tile {k['k_tile_min']}..{k['k_tile_max']} step-kernel {k['step_minus_render_kernel_ms']}  "
           f"e2e {r['e2e']['ms_per_step']} ms  check {r['frame_check']['host_frame_equals_oracle']}/{r['frame_check']['device_frames_equal_oracle']}")
     for w, s in (r.get("scale_8k") or {}).items():
         base.setdefault(w, s["ms_per_step"] * n)
