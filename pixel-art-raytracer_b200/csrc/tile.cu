@@ -55,7 +55,7 @@ namespace par {
 #define PAR_TILE_MIN_CTAS 5
 #endif
 #ifndef PAR_TILE_LIST_CAP
-#define PAR_TILE_LIST_CAP 448
+#define PAR_TILE_LIST_CAP 384
 #endif
 namespace {
 
@@ -69,7 +69,10 @@ constexpr int kListCap = PAR_TILE_LIST_CAP;     // boxes in the shared list (two
 #endif
 constexpr int kHashBits = PAR_TILE_HASH_BITS;
 constexpr int kHashSize = 1 << kHashBits;       // de-duplication set
-constexpr int kOccCap = 512;                    // occupied bins found by the walks of one round
+#ifndef PAR_TILE_OCC_CAP
+#define PAR_TILE_OCC_CAP 896
+#endif
+constexpr int kOccCap = PAR_TILE_OCC_CAP;       // occupied bins found by the walks of one round
 constexpr int kSegMax = 32;                     // (group, light, step range) segments per round
 constexpr int kSegStart = 10;                   // ... of a many-light tile's first round (then adaptive)
 constexpr int kGroupMax = 64;                   // z-groups handled per pass over the tile
@@ -94,6 +97,7 @@ struct Seg {
     int ka, kb;        // step range [ka, kb) covered by this segment
     int item0;         // first walk-phase work item
     int count;         // boxes found (before de-duplication)
+    int occ;           // occupied bins found
     int base;          // first slot of the segment in the box list
     int fill;          // boxes stored (after de-duplication and cull)
     int octant;        // >= 0: every ray of the group has this sign octant (bit a = component a negative) and
@@ -604,7 +608,7 @@ k_tile(const __grid_constant__ TileParams p) {
         // ---- rounds over (group, light, step range) segments; segment index = group * n_lights + light ----
         const int n_seg_total = n_groups * n_lights;
         int s_cur = 0, ka_cur = 0;  // next unprocessed step of segment s_cur
-        int kb_try = -1;            // trial end of the first segment (-1 = the whole walk)
+        int step_cap = INT_MAX;     // most steps of the first segment a round tries (INT_MAX = the whole walk)
         int nseg_try = seg_budget;
 #pragma unroll 1
         while (s_cur < n_seg_total) {
@@ -631,8 +635,9 @@ k_tile(const __grid_constant__ TileParams p) {
                     g.grp = grp;
                     g.start = flat_bin(d, bx, ty, G.gz);  // start bin of every pixel of the group (alternative.cpp:724-727)
                     g.ka = tid == 0 ? ka_cur : 0;
-                    g.kb = (tid == 0 && kb_try >= 0) ? kb_try : g.steps;
+                    g.kb = (tid == 0 && step_cap < g.steps - g.ka) ? g.ka + step_cap : g.steps;
                     g.count = 0;
+                    g.occ = 0;
                     g.fill = 0;
                     g.octant = group_octant(G, lt);
                     my_steps = g.kb - g.ka;
@@ -715,7 +720,7 @@ k_tile(const __grid_constant__ TileParams p) {
                     }
                     // the 4-bit counts of the sub-chunk, in batches of 8 independent loads; occupied bins
                     // go straight to the shared list
-                    int boxes = 0;
+                    int boxes = 0, bins = 0;
                     for (int i0 = 0; i0 < n; i0 += 8) {
                         int f[8], c[8];
 #pragma unroll
@@ -732,9 +737,13 @@ k_tile(const __grid_constant__ TileParams p) {
                                     s.r.occ_meta[o] = (unsigned char)(q << 3 | c[u]);
                                 }
                                 boxes += c[u];
+                                bins++;
                             }
                     }
-                    if (boxes) atomicAdd(&s.seg[q].count, boxes);
+                    if (boxes) {
+                        atomicAdd(&s.seg[q].count, boxes);
+                        atomicAdd(&s.seg[q].occ, bins);
+                    }
                 }
             }
             __syncthreads();
@@ -746,18 +755,27 @@ k_tile(const __grid_constant__ TileParams p) {
             // de-duplication and the shaft cull a segment keeps a small fraction of its candidates,
             // so each of the n_fit segments gets room for min(candidates, kListCap / n_fit) boxes;
             // if one needs more, the round is redone with half the segments.
-            int n_fit = 0, cand_total = 0;
-            while (n_fit < nseg && cand_total + s.seg[n_fit].count <= kHashSize * 3 / 4) {
+            constexpr int kSetCap = kHashSize * 3 / 4;
+            int n_fit = 0, cand_total = 0, occ_total = 0;
+            while (n_fit < nseg && cand_total + s.seg[n_fit].count <= kSetCap && occ_total + s.seg[n_fit].occ <= kOccCap) {
                 cand_total += s.seg[n_fit].count;
+                occ_total += s.seg[n_fit].occ;
                 n_fit++;
             }
-            if (n_fit == 0 || n_occ > kOccCap) {  // shrink: fewer segments first, then fewer steps of the first one
-                if (nseg > 1) {
-                    nseg_try = max(1, nseg / 2);
-                } else {
-                    const int ka = s.seg[0].ka, kb = s.seg[0].kb;
-                    kb_try = ka + max(1, (kb - ka) / 2);
-                }
+            // A trial that does not fit is walked again — with what the failed walk measured, so that one more
+            // walk is enough: the leading segments that do fit, or, when even the first one alone is too much, the
+            // part of its step range that its candidate / occupied-bin density allows.
+            if (n_fit == 0) {
+                const int range = s.seg[0].kb - s.seg[0].ka;
+                const float need = fmaxf((float)s.seg[0].count / (float)kSetCap, (float)s.seg[0].occ / (float)kOccCap);
+                step_cap = max(1, min(range - 1, (int)((float)range * 0.85f / need)));
+                nseg_try = 1;
+                if (kChecks && p.phase_cycles && tid == 0) atomicAdd(&p.phase_cycles[13], 1ull);  // debug: walks thrown away
+                continue;
+            }
+            if (n_occ > kOccCap) {  // the occupied-bin list is incomplete (which bins got a slot is arbitrary)
+                nseg_try = n_fit;
+                if (kChecks && p.phase_cycles && tid == 0) atomicAdd(&p.phase_cycles[15], 1ull);
                 continue;
             }
             const int share = kListCap / n_fit;
@@ -845,11 +863,11 @@ k_tile(const __grid_constant__ TileParams p) {
             __syncthreads();
             mark(kPhGather);
             if (s.overflow) {  // some segment kept more than its share: fewer segments, then fewer steps
+                if (kChecks && p.phase_cycles && tid == 0) atomicAdd(&p.phase_cycles[14], 1ull);  // debug: walks + gathers thrown away
                 if (n_fit > 1) {
                     nseg_try = max(1, n_fit / 2);
                 } else {
-                    const int ka = s.seg[0].ka, kb = s.seg[0].kb;
-                    kb_try = ka + max(1, (kb - ka) / 2);
+                    step_cap = max(1, (s.seg[0].kb - s.seg[0].ka) / 2);
                     nseg_try = 1;
                 }
                 continue;
@@ -965,14 +983,22 @@ k_tile(const __grid_constant__ TileParams p) {
                 s_cur += n_fit - 1;
                 ka_cur = s.seg[n_fit - 1].kb;
             }
-            kb_try = -1;
-            {   // next round's budget: fill ~7/8 of the set at this round's density, and leave the fullest
-                // segment 25 % headroom in its share of the box list
+            {   // next round's budgets, from this round's densities: fill ~7/8 of the de-duplication set and of the
+                // occupied-bin list, and leave the fullest segment 25 % headroom in its share of the box list
                 int max_fill = 1;
                 for (int q = 0; q < n_fit; q++) max_fill = max(max_fill, s.seg[q].fill);
-                const int by_set = (kHashSize * 3 / 4 * 7 / 8) * n_fit / max(cand_total, 1);
+                const int by_set = (kSetCap * 7 / 8) * n_fit / max(cand_total, 1);
+                const int by_occ = (kOccCap * 7 / 8) * n_fit / max(occ_total, 1);
                 const int by_list = kListCap / (max_fill + max_fill / 4 + 1);
-                seg_budget = max(1, min(kSegMax, min(by_set, by_list)));
+                seg_budget = max(1, min(kSegMax, min(min(by_set, by_occ), by_list)));
+                // a split light goes on with the step range its density so far allows; a new light tries its whole walk
+                step_cap = INT_MAX;
+                if (!last_seg_done) {
+                    const Seg& g = s.seg[n_fit - 1];
+                    const float need = fmaxf(fmaxf((float)g.count / (float)kSetCap, (float)g.occ / (float)kOccCap),
+                                             (float)(g.fill + g.fill / 4 + 1) / (float)kListCap);
+                    step_cap = max(1, (int)((float)(g.kb - g.ka) * 0.85f / fmaxf(need, 1e-3f)));
+                }
             }
             nseg_try = seg_budget;
         }

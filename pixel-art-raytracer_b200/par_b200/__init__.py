@@ -477,7 +477,8 @@ class Renderer:
         out = np.zeros(16, np.uint64)
         _check(lib().par_debug_phase_timing(self._h, int(enable), _p(out)))
         d = {n: int(out[i]) for i, n in enumerate(self.PHASES)}
-        d.update(boxes_found=int(out[10]), boxes_kept=int(out[11]), rounds=int(out[12]))
+        d.update(boxes_found=int(out[10]), boxes_kept=int(out[11]), rounds=int(out[12]),
+                 retries_walk=int(out[13]), retries_gather=int(out[14]), retries_occ=int(out[15]))
         return d
 
     def stats(self):

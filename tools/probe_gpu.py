@@ -32,17 +32,18 @@ def run(name, W, H, L, boxes, lights, reps=5):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s = torch.cuda.ExternalStream(r.stream())
         a.record(s)
-        for _ in range(20):
+        n_rep = 200 if W * H <= 3840 * 2160 and len(lights) == 1 else 20
+        for _ in range(n_rep):
             r.render_resident(lights)
         b.record(s)
         r.sync()
-        best["resident_step_ms"] = round(a.elapsed_time(b) / 20, 4)
+        best["resident_step_ms"] = round(a.elapsed_time(b) / n_rep, 4)
         best["config"] = name
         if os.environ.get("PAR_PHASES"):
             r.phase_timing(True)
             r.render_device(lights)
             ph = r.phase_timing(False)
-            extra = {k: ph.pop(k) for k in ("boxes_found", "boxes_kept", "rounds")}
+            extra = {k: ph.pop(k) for k in ("boxes_found", "boxes_kept", "rounds", "retries_walk", "retries_gather", "retries_occ")}
             tot = sum(ph.values()) or 1
             best["phases_pct"] = {k: round(100.0 * v / tot, 1) for k, v in ph.items()}
             best["lists"] = extra
