@@ -830,6 +830,7 @@ k_tile(const __grid_constant__ TileParams p) {
                         h = (h + 1) & (kHashSize - 1);
                     }
                     if (!fresh_key) continue;
+                    if (kChecks && p.phase_cycles) atomicAdd(&p.phase_cycles[9], 1ull);  // debug: candidates after de-duplication
                     const Box b = unpack_box(__ldg(&p.boxes[ent]));
                     const Seg& sg = s.seg[q];
                     const Grp& G = s.grp[sg.grp];

@@ -470,7 +470,7 @@ class Renderer:
         _check(lib().par_get_grid(self._h, _p(count), _p(ids)))
         return count, ids.reshape(V, 8)
 
-    PHASES = ["primary", "group", "setup", "walk", "gather", "shade", "tail", "p7", "p8", "p9"]
+    PHASES = ["primary", "group", "setup", "walk", "gather", "shade", "tail", "p7", "p8"]
 
     def phase_timing(self, enable=True):
         """Debug: per-phase cycle totals of k_shade since the last call (dict), then (re)arm."""
@@ -478,7 +478,7 @@ class Renderer:
         _check(lib().par_debug_phase_timing(self._h, int(enable), _p(out)))
         d = {n: int(out[i]) for i, n in enumerate(self.PHASES)}
         d.update(boxes_found=int(out[10]), boxes_kept=int(out[11]), rounds=int(out[12]),
-                 retries_walk=int(out[13]), retries_gather=int(out[14]), retries_occ=int(out[15]))
+                 retries_walk=int(out[13]), retries_gather=int(out[14]), retries_occ=int(out[15]), boxes_unique=int(out[9]))
         return d
 
     def stats(self):

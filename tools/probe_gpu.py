@@ -43,7 +43,7 @@ def run(name, W, H, L, boxes, lights, reps=5):
             r.phase_timing(True)
             r.render_device(lights)
             ph = r.phase_timing(False)
-            extra = {k: ph.pop(k) for k in ("boxes_found", "boxes_kept", "rounds", "retries_walk", "retries_gather", "retries_occ")}
+            extra = {k: ph.pop(k) for k in ("boxes_found", "boxes_kept", "rounds", "retries_walk", "retries_gather", "retries_occ", "boxes_unique")}
             tot = sum(ph.values()) or 1
             best["phases_pct"] = {k: round(100.0 * v / tot, 1) for k, v in ph.items()}
             best["lists"] = extra
@@ -104,5 +104,6 @@ if __name__ == "__main__":
         run("C3 synthetic 10k/16 lights 3840x2160", 3840, 2160, 2160, *par.scene_synthetic(3840, 2160, 2160))
     if "c5" in which:
         run("C5 synthetic 10k/16 lights 7680x4320", 7680, 4320, 4320, *par.scene_synthetic(7680, 4320, 4320))
+    if "c5" in which or "c5b" in which:
         run("C5b synthetic 40k/16 lights 7680x4320", 7680, 4320, 4320,
             *par.scene_synthetic(7680, 4320, 4320, n=40000))
