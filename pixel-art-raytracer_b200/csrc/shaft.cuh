@@ -1,5 +1,5 @@
 // shaft.cuh — exact-output cull of candidate occluders for a whole group of shadow rays
-// (shared by walks.cu and shade.cu).
+// (tile.cu; compiled for the host by tests/test_shaft_cull_property.py).
 #pragma once
 #include "par_device.cuh"
 
@@ -15,21 +15,45 @@ namespace par {
 // the reference's formula — no pixel of the group can pass the reference's test and the box is
 // dropped.  Axes on which some pixel may have a zero direction component (0 in [L-oh, L-ol])
 // impose no constraint, which also covers every NaN/inf case (quirk Q13) conservatively.
-__device__ __forceinline__ bool shaft_may_hit(const float lo[3], const float hi[3], const float L[3],
-                                              const float ol[3], const float oh[3]) {
-    float smin = -INFINITY, smax = INFINITY;
+// The part that does not depend on the box, once per (group, light): the reciprocals of the light's distance to
+// both ends of the origin interval, and the axes that impose no constraint.
+__device__ __forceinline__ unsigned shaft_prepare(const float L[3], const float ol[3], const float oh[3], float rl[3],
+                                                  float rh[3]) {
+    unsigned free_axes = 0u;
 #pragma unroll
     for (int a = 0; a < 3; a++) {
         const float dl = L[a] - oh[a], dh = L[a] - ol[a];
-        if (dl <= 0.f && dh >= 0.f) continue;
-        // approximate reciprocals (2 ulp) are plenty under the 1e-4 margin
-        const float rl = __fdividef(1.f, dl), rh = __fdividef(1.f, dh);
-        const float v0 = (lo[a] - ol[a]) * rh, v1 = (lo[a] - oh[a]) * rl;
-        const float v2 = (hi[a] - ol[a]) * rh, v3 = (hi[a] - oh[a]) * rl;
+        if (dl <= 0.f && dh >= 0.f) {
+            free_axes |= 1u << a;
+            rl[a] = rh[a] = 0.f;
+        } else {  // approximate reciprocals (2 ulp) are plenty under the 1e-4 margin
+            rl[a] = __fdividef(1.f, dl);
+            rh[a] = __fdividef(1.f, dh);
+        }
+    }
+    return free_axes;
+}
+
+__device__ __forceinline__ bool shaft_may_hit_prepared(const float lo[3], const float hi[3], const float ol[3],
+                                                       const float oh[3], const float rl[3], const float rh[3],
+                                                       unsigned free_axes) {
+    float smin = -INFINITY, smax = INFINITY;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        if ((free_axes >> a) & 1u) continue;
+        const float v0 = (lo[a] - ol[a]) * rh[a], v1 = (lo[a] - oh[a]) * rl[a];
+        const float v2 = (hi[a] - ol[a]) * rh[a], v3 = (hi[a] - oh[a]) * rl[a];
         smin = fmaxf(smin, fminf(fminf(v0, v1), fminf(v2, v3)));
         smax = fminf(smax, fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)));
     }
     return !(smin > smax + 1e-4f * (1.f + fabsf(smin) + fabsf(smax)));
+}
+
+__device__ __forceinline__ bool shaft_may_hit(const float lo[3], const float hi[3], const float L[3],
+                                              const float ol[3], const float oh[3]) {
+    float rl[3], rh[3];
+    const unsigned free_axes = shaft_prepare(L, ol, oh, rl, rh);
+    return shaft_may_hit_prepared(lo, hi, ol, oh, rl, rh, free_axes);
 }
 
 }  // namespace par

@@ -102,6 +102,8 @@ struct Seg {
     int fill;          // boxes stored (after de-duplication and cull)
     int octant;        // >= 0: every ray of the group has this sign octant (bit a = component a negative) and
                        // the boxes are stored as (near, far) corners; -1: mixed, boxes stored as (lo, hi)
+    float rl[3], rh[3];  // shaft cull, the part that does not depend on the box (shaft_prepare)
+    int cull;            // bits 0-2: axes without a constraint; 8: no cull for this segment
 };
 
 struct Grp {
@@ -614,7 +616,16 @@ k_tile(const __grid_constant__ TileParams p) {
         while (s_cur < n_seg_total) {
             __syncthreads();  // previous round fully consumed (lists, segments, pixel lists complete)
             // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
-            const int nseg = min(nseg_try, n_seg_total - s_cur);
+            int nseg = min(nseg_try, n_seg_total - s_cur);
+            {   // Only the LAST segment of a round may cover part of its walk (the advance below relies on it), and the
+                // step cap applies to the first one: a round whose first segment is cut short holds nothing else.
+                const int grp0 = s_cur / n_lights;
+                const short4 lt0 = p.lights[s_cur - grp0 * n_lights];
+                const float dx0 = (float)(lt0.x / kBin) - (float)bx, dy0 = (float)((d.H - lt0.y - lt0.z) / kBin) - (float)ty;
+                const float dz0 = (float)(lt0.z / kBin) - (float)s.grp[grp0].gz;
+                const int steps0 = (int)fmaxf(fmaxf(fabsf(dx0), fabsf(dy0)), fabsf(dz0));
+                if (step_cap < steps0 - ka_cur) nseg = 1;
+            }
             if (tid < 32) {  // warp 0: one lane per segment (kSegMax == 32)
                 int my_steps = 0;
                 if (tid < nseg) {
@@ -659,6 +670,31 @@ k_tile(const __grid_constant__ TileParams p) {
                     s.n_occ = 0;
                     s.overflow = 0;
                 }
+            }
+            if (tid >= 32 && tid < 32 + nseg) {  // warp 1, beside warp 0: the box-independent part of the shaft cull
+                const int sidx = s_cur + tid - 32;
+                const int grp = sidx / n_lights;
+                const Grp& G = s.grp[grp];
+                const short4 lt = p.lights[sidx - grp * n_lights];
+                // Bounds of the group's ray origins.  The origin is cast to short in the reference
+                // (alternative.cpp:720-722): only cull when nothing can wrap.
+                bool can_cull = !(p.debug_flags & 1);
+                float ol[3], oh[3], rl[3], rh[3];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    ol[a] = (float)G.omin[a];
+                    oh[a] = (float)G.omax[a];
+                    can_cull = can_cull && G.omin[a] >= -32768 && G.omax[a] <= 32767;
+                }
+                const float lp[3] = {(float)lt.x, (float)lt.y, (float)lt.z};
+                const unsigned free_axes = shaft_prepare(lp, ol, oh, rl, rh);
+                Seg& g = s.seg[tid - 32];
+#pragma unroll
+                for (int a = 0; a < 3; a++) {
+                    g.rl[a] = rl[a];
+                    g.rh[a] = rh[a];
+                }
+                g.cull = can_cull ? (int)free_axes : 8;
             }
             for (int t = tid; t < kHashSize; t += kT) s.r.hash[t] = kEmpty;
             __syncthreads();
@@ -731,7 +767,7 @@ k_tile(const __grid_constant__ TileParams p) {
 #pragma unroll
                         for (int u = 0; u < 8; u++)
                             if (c[u]) {
-                                const int o = atomicAdd(&s.n_occ, 1);
+                                const int o = atomicAdd(&s.n_occ, 1);  // (warp-aggregating these was 7 % slower)
                                 if (o < kOccCap) {
                                     s.r.occ_bin[o] = (unsigned)f[u];
                                     s.r.occ_meta[o] = (unsigned char)(q << 3 | c[u]);
@@ -789,7 +825,16 @@ k_tile(const __grid_constant__ TileParams p) {
             // counts and expands them into (bin, slot) pairs with shuffles, so that the dependent
             // loads (entity id -> box) run with dense lanes: entity -> de-duplicate -> box ->
             // shaft cull -> the segment's part of the box list.
-            const bool cull_on = !(p.debug_flags & 1);
+            int seg_base = lane < n_fit ? min(s.seg[lane].count, share) : 0;  // lane q: first list slot of segment q
+            {
+                const int own = seg_base;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, seg_base, o);
+                    if (lane >= o) seg_base += t;
+                }
+                seg_base -= own;
+            }
             for (int ob = tid - lane; ob < n_occ; ob += kT) {
                 const bool have = ob + lane < n_occ;
                 const unsigned my_bin = have ? s.r.occ_bin[ob + lane] : 0u;
@@ -815,8 +860,9 @@ k_tile(const __grid_constant__ TileParams p) {
                     const unsigned meta = __shfl_sync(0xffffffffu, my_meta, src);
                     const int cnt_src = __shfl_sync(0xffffffffu, my_c, src);
                     const int slot_i = t - (__shfl_sync(0xffffffffu, incl, src) - cnt_src);
-                    if (t >= total) continue;
                     const int q = meta >> 3;
+                    const int base = __shfl_sync(0xffffffffu, seg_base, q & 31);
+                    if (t >= total) continue;
                     const int ent = __ldg(&p.ids[(size_t)bin * kSlots + slot_i]);
                     const unsigned key = (unsigned)q << 26 | (unsigned)ent;
                     unsigned h = (key * 2654435761u) >> (32 - kHashBits);
@@ -834,25 +880,14 @@ k_tile(const __grid_constant__ TileParams p) {
                     const Box b = unpack_box(__ldg(&p.boxes[ent]));
                     const Seg& sg = s.seg[q];
                     const Grp& G = s.grp[sg.grp];
-                    // Shaft cull against the bounds of the group's ray origins.  The origin is cast to short in
-                    // the reference (alternative.cpp:720-722): only cull when nothing can wrap.
-                    bool can_cull = cull_on;
-                    float org_lo[3], org_hi[3];
-#pragma unroll
-                    for (int a = 0; a < 3; a++) {
-                        org_lo[a] = (float)G.omin[a];
-                        org_hi[a] = (float)G.omax[a];
-                        can_cull = can_cull && G.omin[a] >= -32768 && G.omax[a] <= 32767;
-                    }
-                    if (can_cull) {
-                        const short4 lt = p.lights[sg.light];
+                    if (!(sg.cull & 8)) {  // shaft cull: no ray of the group can hit this box
                         const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
                         const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
-                        const float lp[3] = {(float)lt.x, (float)lt.y, (float)lt.z};
-                        if (!shaft_may_hit(blo, bhi, lp, org_lo, org_hi)) continue;
+                        const float ol[3] = {(float)G.omin[0], (float)G.omin[1], (float)G.omin[2]};
+                        const float oh[3] = {(float)G.omax[0], (float)G.omax[1], (float)G.omax[2]};
+                        const float rl[3] = {sg.rl[0], sg.rl[1], sg.rl[2]}, rh[3] = {sg.rh[0], sg.rh[1], sg.rh[2]};
+                        if (!shaft_may_hit_prepared(blo, bhi, ol, oh, rl, rh, (unsigned)sg.cull)) continue;
                     }
-                    int base = 0;
-                    for (int r = 0; r < q; r++) base += min(s.seg[r].count, share);
                     const int nth = atomicAdd(&s.seg[q].fill, 1);
                     if (nth >= min(sg.count, share)) {
                         s.overflow = 1;

@@ -317,6 +317,31 @@ def test_quirk_light_outside_grid_and_far_away(par, oracle):
     _assert_frame_equal(got, ref)
 
 
+@pytest.mark.parametrize("seed", [11, 12])
+def test_dense_scene_many_lights_split_walks(par, oracle, seed):
+    """Rounds of the render kernel under pressure: a dense scene (every bin along a walk occupied, several
+    entities per bin) and 12 lights — some far outside the grid — so that walks overflow the occupied-bin list
+    and the de-duplication set, are cut into step ranges, re-walked with measured densities and mixed with
+    whole walks of the following lights.  Every (pixel, light) term must still be there exactly once."""
+    from par_b200 import AABB, LIGHT
+    rng = np.random.default_rng(seed)
+    W, H, L = 1200, 440, 440
+    n = 9000
+    boxes = np.zeros(n, AABB)
+    boxes["px"] = rng.integers(0, W - 20, n)
+    boxes["py"] = rng.integers(0, 260, n)
+    boxes["pz"] = rng.integers(0, L - 20, n)
+    boxes["ex"] = boxes["ey"] = boxes["ez"] = 20
+    lights = np.zeros(12, LIGHT)
+    lights["x"] = rng.integers(-2500, 4000, 12)
+    lights["y"] = rng.integers(20, 700, 12)
+    lights["z"] = rng.integers(-1500, 2500, 12)
+    lights["x"][:4] = rng.integers(0, W, 4)  # some inside the view
+    lights["z"][:4] = rng.integers(0, L, 4)
+    got, ref = _render_both(par, oracle, W, H, L, boxes, lights, check_grid=False)
+    _assert_frame_equal(got, ref)
+
+
 def test_empty_and_degenerate_scenes(par, oracle):
     from par_b200 import AABB, LIGHT
     got, ref = _render_both(par, oracle, 480, 320, 320, np.zeros(0, AABB), par.light_default())
