@@ -29,10 +29,10 @@
 //        walk    one thread per run of steps: the fp32 position chain is accumulated sequentially
 //                exactly as the reference does (Q15); the 7 probes of a step collapse to the
 //                distinct bins among them; 4-bit counts fetched as batches of independent loads;
-//        gather  a warp scan expands the occupied bins into dense (bin, slot) lanes: entity ->
-//                de-duplicate per segment (shared hash set; testing a box twice cannot change an
-//                OR) -> box -> shaft cull (shaft.cuh) -> float corners in the segment's share of a
-//                shared box list;
+//        gather  a warp scan expands the occupied bins into dense (bin, slot) lanes: entity -> box ->
+//                shaft cull (shaft.cuh) -> de-duplicate the survivors per segment (shared hash set;
+//                testing a box twice cannot change an OR) -> float corners in the segment's share of
+//                a shared box list;
 //        shade   one lane per pixel of the round's groups: per light the L1-normalised direction
 //                (Q12), the Lambert term and — only when it is > 0 (Q19) — the slab tests of that
 //                segment's boxes with unbounded-line semantics (Q14), self-entity skip (Q17) and
@@ -148,6 +148,7 @@ struct TileSmem {
     int gmin;
     int n_occ;
     int overflow;
+    int n_keys;   // entries of the de-duplication set
     int n_items;
     int run;
 };
@@ -669,6 +670,7 @@ k_tile(const __grid_constant__ TileParams p) {
                     s.run = run;
                     s.n_occ = 0;
                     s.overflow = 0;
+                    s.n_keys = 0;
                 }
             }
             if (tid >= 32 && tid < 32 + nseg) {  // warp 1, beside warp 0: the box-independent part of the shaft cull
@@ -786,24 +788,22 @@ k_tile(const __grid_constant__ TileParams p) {
             mark(kPhWalk);
             const int n_occ = s.n_occ;  // every occupied bin holds >= 1 box, so n_occ <= sum of counts
             // D. how many leading segments go into this round?  (every thread, redundantly)
-            // The de-duplication set must stay sparse (candidates <= 3/4 of its slots) and the
-            // occupied-bin list must be complete.  The box list itself is shared out evenly: after
-            // de-duplication and the shaft cull a segment keeps a small fraction of its candidates,
-            // so each of the n_fit segments gets room for min(candidates, kListCap / n_fit) boxes;
-            // if one needs more, the round is redone with half the segments.
+            // The occupied-bin list must be complete for them.  Candidates do not limit a round: the gather culls
+            // before it de-duplicates, so the set only ever holds survivors (its fill and the box list are checked
+            // while gathering; a round that overflows either is redone with half the segments).
             constexpr int kSetCap = kHashSize * 3 / 4;
             int n_fit = 0, cand_total = 0, occ_total = 0;
-            while (n_fit < nseg && cand_total + s.seg[n_fit].count <= kSetCap && occ_total + s.seg[n_fit].occ <= kOccCap) {
+            while (n_fit < nseg && occ_total + s.seg[n_fit].occ <= kOccCap) {
                 cand_total += s.seg[n_fit].count;
                 occ_total += s.seg[n_fit].occ;
                 n_fit++;
             }
             // A trial that does not fit is walked again — with what the failed walk measured, so that one more
             // walk is enough: the leading segments that do fit, or, when even the first one alone is too much, the
-            // part of its step range that its candidate / occupied-bin density allows.
+            // part of its step range that its occupied-bin density allows.
             if (n_fit == 0) {
                 const int range = s.seg[0].kb - s.seg[0].ka;
-                const float need = fmaxf((float)s.seg[0].count / (float)kSetCap, (float)s.seg[0].occ / (float)kOccCap);
+                const float need = (float)s.seg[0].occ / (float)kOccCap;
                 step_cap = max(1, min(range - 1, (int)((float)range * 0.85f / need)));
                 nseg_try = 1;
                 if (kChecks && p.phase_cycles && tid == 0) atomicAdd(&p.phase_cycles[13], 1ull);  // debug: walks thrown away
@@ -814,10 +814,15 @@ k_tile(const __grid_constant__ TileParams p) {
                 if (kChecks && p.phase_cycles && tid == 0) atomicAdd(&p.phase_cycles[15], 1ull);
                 continue;
             }
-            const int share = kListCap / n_fit;
+            // List room of a segment: in proportion to its candidates (a segment keeps a small, similar fraction of
+            // them after de-duplication and cull); the sum stays within the list.
+            auto share_of = [&](int q) -> int {
+                const int c = s.seg[q].count;
+                return min(c, (int)((long long)(kListCap - n_fit) * c / max(cand_total, 1)) + 1);
+            };
             if (tid < n_fit) {  // base of segment tid in the box list (read after the next barrier)
                 int base = 0;
-                for (int q = 0; q < tid; q++) base += min(s.seg[q].count, share);
+                for (int q = 0; q < tid; q++) base += share_of(q);
                 s.seg[tid].base = base;
             }
 
@@ -825,7 +830,7 @@ k_tile(const __grid_constant__ TileParams p) {
             // counts and expands them into (bin, slot) pairs with shuffles, so that the dependent
             // loads (entity id -> box) run with dense lanes: entity -> de-duplicate -> box ->
             // shaft cull -> the segment's part of the box list.
-            int seg_base = lane < n_fit ? min(s.seg[lane].count, share) : 0;  // lane q: first list slot of segment q
+            int seg_base = lane < n_fit ? share_of(lane) : 0;  // lane q: first list slot of segment q
             {
                 const int own = seg_base;
 #pragma unroll
@@ -864,32 +869,38 @@ k_tile(const __grid_constant__ TileParams p) {
                     const int base = __shfl_sync(0xffffffffu, seg_base, q & 31);
                     if (t >= total) continue;
                     const int ent = __ldg(&p.ids[(size_t)bin * kSlots + slot_i]);
-                    const unsigned key = (unsigned)q << 26 | (unsigned)ent;
-                    unsigned h = (key * 2654435761u) >> (32 - kHashBits);
-                    bool fresh_key;
-                    for (;;) {
-                        const unsigned old = atomicCAS(&s.r.hash[h], kEmpty, key);
-                        if (old == kEmpty || old == key) {
-                            fresh_key = old == kEmpty;
-                            break;
-                        }
-                        h = (h + 1) & (kHashSize - 1);
-                    }
-                    if (!fresh_key) continue;
-                    if (kChecks && p.phase_cycles) atomicAdd(&p.phase_cycles[9], 1ull);  // debug: candidates after de-duplication
-                    const Box b = unpack_box(__ldg(&p.boxes[ent]));
                     const Seg& sg = s.seg[q];
                     const Grp& G = s.grp[sg.grp];
-                    if (!(sg.cull & 8)) {  // shaft cull: no ray of the group can hit this box
+                    auto shaft_culled = [&](const Box& b) -> bool {  // no ray of the group can hit this box
+                        if (sg.cull & 8) return false;
                         const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
                         const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
                         const float ol[3] = {(float)G.omin[0], (float)G.omin[1], (float)G.omin[2]};
                         const float oh[3] = {(float)G.omax[0], (float)G.omax[1], (float)G.omax[2]};
                         const float rl[3] = {sg.rl[0], sg.rl[1], sg.rl[2]}, rh[3] = {sg.rh[0], sg.rh[1], sg.rh[2]};
-                        if (!shaft_may_hit_prepared(blo, bhi, ol, oh, rl, rh, (unsigned)sg.cull)) continue;
+                        return !shaft_may_hit_prepared(blo, bhi, ol, oh, rl, rh, (unsigned)sg.cull);
+                    };
+                    auto first_time = [&]() -> bool {  // (segment, entity) not seen before in this round
+                        const unsigned key = (unsigned)q << 26 | (unsigned)ent;
+                        unsigned h = (key * 2654435761u) >> (32 - kHashBits);
+                        for (;;) {
+                            const unsigned old = atomicCAS(&s.r.hash[h], kEmpty, key);
+                            if (old == kEmpty || old == key) return old == kEmpty;
+                            h = (h + 1) & (kHashSize - 1);
+                        }
+                    };
+                    // cull, then de-duplicate the survivors: the set stays small however many candidates the walks find
+                    const Box b = unpack_box(__ldg(&p.boxes[ent]));
+                    if (shaft_culled(b)) continue;
+                    if (*(volatile int*)&s.overflow) continue;  // (the set may be filling up: the round is redone anyway)
+                    if (!first_time()) continue;
+                    if (atomicAdd(&s.n_keys, 1) >= kHashSize * 3 / 4) {
+                        s.overflow = 1;
+                        continue;
                     }
+                    if (kChecks && p.phase_cycles) atomicAdd(&p.phase_cycles[9], 1ull);  // debug: distinct survivors
                     const int nth = atomicAdd(&s.seg[q].fill, 1);
-                    if (nth >= min(sg.count, share)) {
+                    if (nth >= share_of(q)) {
                         s.overflow = 1;
                         continue;
                     }
@@ -1021,18 +1032,28 @@ k_tile(const __grid_constant__ TileParams p) {
             }
             {   // next round's budgets, from this round's densities: fill ~7/8 of the de-duplication set and of the
                 // occupied-bin list, and leave the fullest segment 25 % headroom in its share of the box list
-                int max_fill = 1;
-                for (int q = 0; q < n_fit; q++) max_fill = max(max_fill, s.seg[q].fill);
-                const int by_set = (kSetCap * 7 / 8) * n_fit / max(cand_total, 1);
-                const int by_occ = (kOccCap * 7 / 8) * n_fit / max(occ_total, 1);
-                const int by_list = kListCap / (max_fill + max_fill / 4 + 1);
+                int max_fill = 1, total_fill = 0;
+                for (int q = 0; q < n_fit; q++) {
+                    max_fill = max(max_fill, s.seg[q].fill);
+                    total_fill += s.seg[q].fill;
+                }
+                const int by_set = (kSetCap * 7 / 8) * n_fit / max(s.n_keys, 1);
+#ifndef PAR_TILE_OCC_FILL
+#define PAR_TILE_OCC_FILL 4  // eighths of the occupied-bin list a round aims at (densities vary a lot from light to light)
+#endif
+                const int by_occ = (kOccCap * PAR_TILE_OCC_FILL / 8) * n_fit / max(occ_total, 1);
+                // (list room is shared out in proportion to the candidates: what counts is the total kept, with headroom
+                // for segments that keep a larger fraction than the others)
+#ifndef PAR_TILE_LIST_FILL
+#define PAR_TILE_LIST_FILL 2  // eighths of the box list
+#endif
+                const int by_list = (kListCap * PAR_TILE_LIST_FILL / 8) * n_fit / max(total_fill, 1);
                 seg_budget = max(1, min(kSegMax, min(min(by_set, by_occ), by_list)));
                 // a split light goes on with the step range its density so far allows; a new light tries its whole walk
                 step_cap = INT_MAX;
                 if (!last_seg_done) {
                     const Seg& g = s.seg[n_fit - 1];
-                    const float need = fmaxf(fmaxf((float)g.count / (float)kSetCap, (float)g.occ / (float)kOccCap),
-                                             (float)(g.fill + g.fill / 4 + 1) / (float)kListCap);
+                    const float need = fmaxf((float)g.occ / (float)kOccCap, (float)(g.fill + g.fill / 4 + 1) / (float)kListCap);
                     step_cap = max(1, (int)((float)(g.kb - g.ka) * 0.85f / fmaxf(need, 1e-3f)));
                 }
             }
