@@ -816,9 +816,9 @@ k_tile(const __grid_constant__ TileParams p) {
             }
             // List room of a segment: in proportion to its candidates (a segment keeps a small, similar fraction of
             // them after de-duplication and cull); the sum stays within the list.
-            auto share_of = [&](int q) -> int {
-                const int c = s.seg[q].count;
-                return min(c, (int)((long long)(kListCap - n_fit) * c / max(cand_total, 1)) + 1);
+            auto share_of = [&](int q) -> int {  // (candidates per round stay far below 2^32 / kListCap)
+                const unsigned c = (unsigned)s.seg[q].count;
+                return (int)min(c, (unsigned)(kListCap - n_fit) * c / (unsigned)max(cand_total, 1) + 1u);
             };
             if (tid < n_fit) {  // base of segment tid in the box list (read after the next barrier)
                 int base = 0;
@@ -830,7 +830,8 @@ k_tile(const __grid_constant__ TileParams p) {
             // counts and expands them into (bin, slot) pairs with shuffles, so that the dependent
             // loads (entity id -> box) run with dense lanes: entity -> de-duplicate -> box ->
             // shaft cull -> the segment's part of the box list.
-            int seg_base = lane < n_fit ? share_of(lane) : 0;  // lane q: first list slot of segment q
+            const int seg_share = lane < n_fit ? share_of(lane) : 0;  // lane q: list room of segment q ...
+            int seg_base = seg_share;                                  // ... and its first list slot
             {
                 const int own = seg_base;
 #pragma unroll
@@ -852,8 +853,12 @@ k_tile(const __grid_constant__ TileParams p) {
                     if (lane >= o) incl += t;
                 }
                 const int total = __shfl_sync(0xffffffffu, incl, 31);
-                for (int t0 = 0; t0 < total; t0 += 32) {
-                    const int t = t0 + lane;
+                // One candidate: where it sits (a binary search over the warp's prefix sums, all lanes together), then
+                // entity id -> box -> cull -> de-duplicate -> list.
+                struct Cand {
+                    int ent, q, base, room;
+                };
+                auto locate = [&](int t) -> Cand {  // convergent; ent < 0: no candidate t
                     int src = 0;  // first lane whose inclusive prefix exceeds t
 #pragma unroll
                     for (int step = 16; step; step >>= 1) {
@@ -865,46 +870,51 @@ k_tile(const __grid_constant__ TileParams p) {
                     const unsigned meta = __shfl_sync(0xffffffffu, my_meta, src);
                     const int cnt_src = __shfl_sync(0xffffffffu, my_c, src);
                     const int slot_i = t - (__shfl_sync(0xffffffffu, incl, src) - cnt_src);
-                    const int q = meta >> 3;
-                    const int base = __shfl_sync(0xffffffffu, seg_base, q & 31);
-                    if (t >= total) continue;
-                    const int ent = __ldg(&p.ids[(size_t)bin * kSlots + slot_i]);
+                    Cand c;
+                    c.q = meta >> 3;
+                    c.base = __shfl_sync(0xffffffffu, seg_base, c.q & 31);
+                    c.room = __shfl_sync(0xffffffffu, seg_share, c.q & 31);
+                    c.ent = t < total ? __ldg(&p.ids[(size_t)bin * kSlots + slot_i]) : -1;
+                    return c;
+                };
+                auto process = [&](const Cand& c, const int4 raw) {
+                    const int q = c.q, ent = c.ent;
                     const Seg& sg = s.seg[q];
                     const Grp& G = s.grp[sg.grp];
-                    auto shaft_culled = [&](const Box& b) -> bool {  // no ray of the group can hit this box
-                        if (sg.cull & 8) return false;
+                    const Box b = unpack_box(raw);
+                    if (!(sg.cull & 8)) {  // shaft cull: no ray of the group can hit this box
                         const float blo[3] = {(float)b.px, (float)b.py, (float)b.pz};
                         const float bhi[3] = {(float)(b.px + b.ex), (float)(b.py + b.ey), (float)(b.pz + b.ez)};
                         const float ol[3] = {(float)G.omin[0], (float)G.omin[1], (float)G.omin[2]};
                         const float oh[3] = {(float)G.omax[0], (float)G.omax[1], (float)G.omax[2]};
                         const float rl[3] = {sg.rl[0], sg.rl[1], sg.rl[2]}, rh[3] = {sg.rh[0], sg.rh[1], sg.rh[2]};
-                        return !shaft_may_hit_prepared(blo, bhi, ol, oh, rl, rh, (unsigned)sg.cull);
-                    };
-                    auto first_time = [&]() -> bool {  // (segment, entity) not seen before in this round
-                        const unsigned key = (unsigned)q << 26 | (unsigned)ent;
-                        unsigned h = (key * 2654435761u) >> (32 - kHashBits);
-                        for (;;) {
-                            const unsigned old = atomicCAS(&s.r.hash[h], kEmpty, key);
-                            if (old == kEmpty || old == key) return old == kEmpty;
-                            h = (h + 1) & (kHashSize - 1);
-                        }
-                    };
-                    // cull, then de-duplicate the survivors: the set stays small however many candidates the walks find
-                    const Box b = unpack_box(__ldg(&p.boxes[ent]));
-                    if (shaft_culled(b)) continue;
-                    if (*(volatile int*)&s.overflow) continue;  // (the set may be filling up: the round is redone anyway)
-                    if (!first_time()) continue;
+                        if (!shaft_may_hit_prepared(blo, bhi, ol, oh, rl, rh, (unsigned)sg.cull)) return;
+                    }
+                    // de-duplicate the survivors: the set stays small however many candidates the walks find
+                    if (*(volatile int*)&s.overflow) return;  // (the set may be filling up: the round is redone anyway)
+                    const unsigned key = (unsigned)q << 26 | (unsigned)ent;
+                    unsigned h = (key * 2654435761u) >> (32 - kHashBits);
+                    for (;;) {
+                        const unsigned old = atomicCAS(&s.r.hash[h], kEmpty, key);
+                        if (old == key) return;  // (segment, entity) seen before in this round
+                        if (old == kEmpty) break;
+                        h = (h + 1) & (kHashSize - 1);
+                    }
                     if (atomicAdd(&s.n_keys, 1) >= kHashSize * 3 / 4) {
                         s.overflow = 1;
-                        continue;
+                        return;
                     }
                     if (kChecks && p.phase_cycles) atomicAdd(&p.phase_cycles[9], 1ull);  // debug: distinct survivors
                     const int nth = atomicAdd(&s.seg[q].fill, 1);
-                    if (nth >= share_of(q)) {
+                    if (nth >= c.room) {
                         s.overflow = 1;
-                        continue;
+                        return;
                     }
-                    store_box(s.r.list, base + nth, b, ent, sg.octant);
+                    store_box(s.r.list, c.base + nth, b, ent, sg.octant);
+                };
+                for (int t0 = 0; t0 < total; t0 += 32) {  // (two candidates per lane in flight was 4 % slower)
+                    const Cand c = locate(t0 + lane);
+                    if (c.ent >= 0) process(c, __ldg(&p.boxes[c.ent]));
                 }
             }
             __syncthreads();
