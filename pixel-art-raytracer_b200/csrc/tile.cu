@@ -1040,8 +1040,8 @@ k_tile(const __grid_constant__ TileParams p) {
                 s_cur += n_fit - 1;
                 ka_cur = s.seg[n_fit - 1].kb;
             }
-            {   // next round's budgets, from this round's densities: fill ~7/8 of the de-duplication set and of the
-                // occupied-bin list, and leave the fullest segment 25 % headroom in its share of the box list
+            if (s_cur < n_seg_total) {  // next round's budgets, from this round's densities (aiming well below the
+                                        // capacities: densities vary a lot from light to light)
                 int max_fill = 1, total_fill = 0;
                 for (int q = 0; q < n_fit; q++) {
                     max_fill = max(max_fill, s.seg[q].fill);
