@@ -618,7 +618,8 @@ k_tile(const __grid_constant__ TileParams p) {
             __syncthreads();  // previous round fully consumed (lists, segments, pixel lists complete)
             // A. describe the trial segments (walk set-up, alternative.cpp:406-430)
             int nseg = min(nseg_try, n_seg_total - s_cur);
-            {   // Only the LAST segment of a round may cover part of its walk (the advance below relies on it), and the
+            if (step_cap != INT_MAX) {
+                // Only the LAST segment of a round may cover part of its walk (the advance below relies on it), and the
                 // step cap applies to the first one: a round whose first segment is cut short holds nothing else.
                 const int grp0 = s_cur / n_lights;
                 const short4 lt0 = p.lights[s_cur - grp0 * n_lights];
