@@ -145,6 +145,7 @@ struct TileSmem {
     int cursor[kGroupMax];
     Seg seg[kSegMax];
     unsigned bits[2];
+    int more;     // some pixel's z-group lies beyond the current window of kGroupMax groups
     int gmin;
     int n_occ;
     int overflow;
@@ -460,6 +461,7 @@ k_tile(const __grid_constant__ TileParams p) {
         if (tid == 0) {
             s.gmin = kNoGroup;
             s.bits[0] = s.bits[1] = 0u;
+            s.more = 0;
         }
         __syncthreads();
         int mine = kNoGroup;
@@ -474,22 +476,27 @@ k_tile(const __grid_constant__ TileParams p) {
         // ---- the groups present in [gmin, gmin + 64) ----
         {
             unsigned b0 = 0u, b1 = 0u;
+            bool beyond = false;
 #pragma unroll
             for (int m = 0; m < kPPT; m++) {
                 if (gz[m] == kNoGroup || gz[m] <= g_done) continue;
                 const unsigned rel = (unsigned)(gz[m] - gmin);
                 if (rel < 32u) b0 |= 1u << rel;
                 else if (rel < 64u) b1 |= 1u << (rel - 32u);
+                else beyond = true;
             }
             b0 = __reduce_or_sync(0xffffffffu, b0);
             b1 = __reduce_or_sync(0xffffffffu, b1);
+            beyond = __any_sync(0xffffffffu, beyond);
             if (lane == 0) {
                 if (b0) atomicOr(&s.bits[0], b0);
                 if (b1) atomicOr(&s.bits[1], b1);
+                if (beyond) s.more = 1;
             }
         }
         __syncthreads();
         const unsigned bits0 = s.bits[0], bits1 = s.bits[1];
+        const bool more_windows = s.more != 0;  // else this pass is the tile's last: no further search
         const int n_groups = __popc(bits0) + __popc(bits1);
         auto group_index = [&](int g) -> int {  // index of group g among the present ones, -1 if not in this pass
             if (g == kNoGroup || g <= g_done) return -1;
@@ -1070,6 +1077,7 @@ k_tile(const __grid_constant__ TileParams p) {
             }
             nseg_try = seg_budget;
         }
+        if (!more_windows) break;
         g_done = gmin + (kGroupMax - 1);
     }
 
