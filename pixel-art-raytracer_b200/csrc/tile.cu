@@ -37,9 +37,10 @@
 //                (Q12), the Lambert term and — only when it is > 0 (Q19) — the slab tests of that
 //                segment's boxes with unbounded-line semantics (Q14), self-entity skip (Q17) and
 //                std::min/std::max NaN semantics (Q13) reproduced exactly (three variants, see
-//                slab_hit_*).  Rounds that do not fit the shared lists are split (fewer segments,
-//                then fewer steps of one light); the (acc, shadowed) state of an unfinished pixel
-//                is parked in its own slot of the output frame.
+//                slab_hit_*).  A round that does not fit the shared lists is walked again with what
+//                the failed walk measured (the leading segments that fit, or the step range of one
+//                light that its density allows); the (acc, shadowed) state of an unfinished pixel is
+//                parked in its own slot of the output frame.
 //   Finished RGBA8 pixels are staged in shared memory and leave as 16-byte stores — into the own
 //   frame and, fused frame exchange, in place into the frames of peer GPUs over NVLink.
 // All fp32 arithmetic is IEEE round-to-nearest with no FMA contraction (-fmad=false).
