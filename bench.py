@@ -698,16 +698,19 @@ def ours(args):
     prof = load_json(ROOFLINE_PROFILE, {}) or {}
     cap = (prof.get("kernels") or {}).get(args.workload)
     src_sha = kernel_source_sha()
-    if cap and prof.get("source_sha") == src_sha and world == 1:
-        ex = cap["warp_instructions"] * 32 / (render_ms * 1e-3) / 1e12
+    if cap and prof.get("source_sha") == src_sha:
+        # (N > 1: rank 0 renders its share of the tile rows; the capture is of the whole frame on one GPU)
+        ex = cap["warp_instructions"] * frac_rows * 32 / (render_ms * 1e-3) / 1e12
         roofline.update({"achieved": round(ex, 2), "frac": round(ex / peak_ops, 3),
-                         "warp_instructions_per_launch": cap["warp_instructions"],
-                         "traffic": cap["dram_bytes_read"] + cap["dram_bytes_write"],
+                         "warp_instructions_per_launch": cap["warp_instructions"] * frac_rows,
+                         "traffic": (cap["dram_bytes_read"] + cap["dram_bytes_write"]) if world == 1 else None,
                          "ncu": {k: cap.get(k) for k in ("issue_active_pct", "warps_active_pct", "duration_us_under_ncu",
                                                          "registers_per_thread", "source")},
                          "note": "frac = executed warp instructions (ncu smsp__inst_executed.sum, capture of this very "
                                  "build: source hash matches) x 32 lanes / live CUDA-event kernel time / peak = the "
-                                 "fraction of issue slots the kernel fills"})
+                                 "fraction of issue slots the kernel fills"
+                                 + ("" if world == 1 else f"; at N = {world} the one-GPU capture's count is scaled by rank 0's "
+                                    "share of the tile rows (an estimate: tiles differ in cost)")})
     else:
         roofline["note"] = ("no ncu capture of this build for this workload/N (profiles/roofline_r02.json source hash "
                             f"{prof.get('source_sha')} vs built {src_sha}): hardware fraction not quoted")
