@@ -231,9 +231,19 @@ class Job:
         world, rank, local, dev = env["world"], env["rank"], env["local"], env["dev"]
         self.W, self.H, self.L, self.desc, self.boxes, self.lights = make_workload(par, name)
         self.rays_frame = self.W * self.H * (1 + len(self.lights))
-        self.ren = par.Renderer(self.W, self.H, self.L, device=local, stripe_count=world, stripe_index=rank)
-        self.ren.set_stream(env["stream"].cuda_stream)
-        self.ren.set_atlas()
+        # equal stripe counts per rank (e.g. 108 tile rows over 8 GPUs: half tile rows); the NCCL fallback's
+        # stripe-major staging needs whole tile rows
+        from par_b200.bands import stripe_split_for
+        self.split = 1 if exchange == "nccl" else stripe_split_for(self.W, self.H, world)
+
+        def make_renderer():
+            ren = par.Renderer(self.W, self.H, self.L, device=local, stripe_count=world, stripe_index=rank,
+                               stripe_split=self.split)
+            ren.set_stream(env["stream"].cuda_stream)
+            ren.set_atlas()
+            return ren
+
+        self.ren = make_renderer()
         self.h_boxes = par.pinned_empty(len(self.boxes), par.AABB)
         self.h_boxes[:] = self.boxes
         self.exchange = "none" if world == 1 else exchange
@@ -257,6 +267,10 @@ class Job:
             dist.all_reduce(ok, op=dist.ReduceOp.MIN)
             if int(ok.item()) == 0:
                 self.exchange = "nccl"
+                if self.split > 1:  # the staging frame of the fallback is made of whole tile rows
+                    self.ren.close()
+                    self.split = 1
+                    self.ren = make_renderer()
         if world > 1 and self.exchange == "nccl":
             self.staging = torch.zeros(self.ren.staging_bytes(), dtype=torch.uint8, device=dev)
             self.frame = torch.zeros(self.H * self.W * 4, dtype=torch.uint8, device=dev)
@@ -374,7 +388,7 @@ def series_other(env, args, ops_tab, name):
                "value": round(job.rays_frame * steps / ms / 1e3, 1), "unit": "Mrays/s",
                "frames_per_s": round(1e3 * steps / ms, 2),
                "render_kernel_ms_per_rank": k, "render_kernel_ms_min": min(k), "render_kernel_ms_max": max(k),
-               "scene_loader_ms": ranks[0]["scene_loader_ms"], "exchange": job.exchange,
+               "scene_loader_ms": ranks[0]["scene_loader_ms"], "exchange": job.exchange, "stripe_split": job.split,
                "frame_check": {"oracle_frame_sha256": want,
                                "device_frames_equal_oracle": [r["frame_sha256"] == want for r in ranks
                                                               if r["frame_sha256"] is not None]}}
@@ -491,8 +505,8 @@ def ours(args):
     job = Job(env, args.workload, args.exchange)
     ren, W, H, L, lights, boxes, h_boxes = job.ren, job.W, job.H, job.L, job.lights, job.boxes, job.h_boxes
     n_lights, rays_frame, exchange = len(lights), job.rays_frame, job.exchange
-    from par_b200.bands import owned_rows
-    my_rows = sum(b - a for a, b in owned_rows(H, world, rank))
+    from par_b200.bands import owned_rects
+    my_px = sum((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in owned_rects(W, H, world, rank, job.split))
     trace(f"exchange = {exchange}")
     h_frame = par.pinned_empty((H, W), par.COLOR) if rank == 0 else None
     token = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -689,7 +703,7 @@ def ours(args):
     prop = torch.cuda.get_device_properties(dev)
     sm_max = (clocks or {}).get("sm_max_mhz") or peaks.get("sm_max_mhz") or 1965.0
     peak_ops = prop.multi_processor_count * 128 * sm_max * 1e6 / 1e12  # T lane-ops/s
-    frac_rows = my_rows / H
+    frac_rows = my_px / (W * H)
     roofline = {"bound": "fp32_alu", "kernel": "k_tile (primary rays + shadow walks + shading + RGBA8 pack, one CTA per 40x40 tile)",
                 "unit": "Tlane-op/s", "peak": round(peak_ops, 2),
                 "peak_source": f"{prop.multi_processor_count} SMs x 128 lanes x {sm_max:.0f} MHz = one warp instruction per "
@@ -723,7 +737,7 @@ def ours(args):
                                            "reference's loops execute for this frame) / kernel time; algorithmic_speedup = "
                                            "that / peak, > 1 because one grid walk serves a whole tile x z-group, probes "
                                            "are de-duplicated, the shaft cull drops boxes no ray of a group can hit (Q19)"}
-    hbm_bytes = 4.0 * W * my_rows + 16.0 * len(boxes)
+    hbm_bytes = 4.0 * my_px + 16.0 * len(boxes)
     roofline["hbm"] = {"algorithmic_bytes_per_launch": hbm_bytes,
                        "achieved_gbs": round(hbm_bytes / (render_ms * 1e-3) / 1e9, 1), "peak_gbs": peaks.get("hbm_gbs"),
                        "note": "RGBA8 frame written + scene read (the G-buffer never leaves the SM); not the bound"}
@@ -736,7 +750,7 @@ def ours(args):
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {job.desc}", "view": [W, H, L], "n_entities": int(len(boxes)),
-                   "n_lights": int(n_lights), "rays_per_frame": rays_frame,
+                   "n_lights": int(n_lights), "rays_per_frame": rays_frame, "stripe_split": job.split,
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"interleaved 40-row stripes x{world}, frame exchange fused into the render kernel "
                                    "(peer-memory stores over NVLink, arrival/credit flags in the frame footers, no "

@@ -96,7 +96,12 @@ typedef struct par_config {
     int32_t tile_order;   /* longest-tile-first CTA order from the previous frame's per-tile cost: */
                           /* 0 = automatic (>= 2 lights, or one light when the tiles make 1-3 waves */
                           /* of resident CTAs), 1 = always, -1 = never                              */
-    int32_t reserved[2];
+    int32_t stripe_split; /* > 1: every 40-row tile row is cut into this many stripes of equal width  */
+                          /* (must divide width / 40) and stripe v = tile row * split + segment goes to */
+                          /* rank v % stripe_count: equal stripe counts per rank when height / 40 is not */
+                          /* a multiple of the rank count (e.g. 108 tile rows over 8 GPUs: split 2).     */
+                          /* 0 / 1 = whole tile rows.  Not with the stripe-major staging calls.          */
+    int32_t reserved;
 } par_config;
 
 /* Filled by par_render / par_get_stats; GPU times are CUDA-event milliseconds on the

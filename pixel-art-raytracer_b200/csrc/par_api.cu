@@ -303,16 +303,19 @@ int bad_scene_error(const LoaderCounters& lc) {
 int check_scene_flag(par_ctx* c) { return c->h_ctr->bad_scene ? bad_scene_error(*c->h_ctr) : PAR_OK; }
 
 // Image rows the context renders (its band, restricted to its stripes).
-uint64_t owned_row_count(const par_ctx* c) {
-    uint64_t rows = 0;
+// Pixels the context renders (its band, restricted to its stripes).
+uint64_t owned_pixel_count(const par_ctx* c) {
+    uint64_t px = 0;
     int first, count;
     owned_tile_rows(c->d, first, count);
-    for (int t = first, q = 0; q < count; q++, t += c->d.stripe_n) {
+    const int seg = stripe_segments(c->d);
+    for (int v = first, q = 0; q < count; q++, v += c->d.stripe_n) {
+        const int t = v / seg;
         const int a = t * kBin > c->d.row0 ? t * kBin : c->d.row0;
         const int b = (t + 1) * kBin < c->d.row1 ? (t + 1) * kBin : c->d.row1;
-        rows += (uint64_t)(b - a);
+        px += (uint64_t)(b - a) * (uint64_t)(c->d.W / seg);
     }
-    return rows;
+    return px;
 }
 
 void free_grid(GridBuffers& g) {
@@ -350,6 +353,10 @@ int par_create(par_ctx** out, const par_config* cfg) {
     if (cfg->stripe_count < 0 || cfg->stripe_count > 64 ||
         (cfg->stripe_count > 1 && (cfg->stripe_index < 0 || cfg->stripe_index >= cfg->stripe_count)))
         return fail(PAR_ERR_INVALID_ARG, "par_create: bad stripe_count / stripe_index%s%s");
+    const int split = cfg->stripe_split > 1 ? cfg->stripe_split : 1;
+    if (cfg->stripe_split < 0 || split > 8 || (cfg->width / B) % split != 0 || (split > 1 && cfg->stripe_count < 2))
+        return fail(PAR_ERR_INVALID_ARG,
+                    "par_create: stripe_split must be 0..8, divide width / 40 and go with stripe_count >= 2%s%s");
     int n_dev = 0;
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
         cudaGetLastError();
@@ -383,6 +390,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
     d.row1 = row1;
     d.stripe_n = cfg->stripe_count > 1 ? cfg->stripe_count : 1;
     d.stripe_i = cfg->stripe_count > 1 ? cfg->stripe_index : 0;
+    d.stripe_s = split;
 
     DeviceGuard guard(cfg->device);
     int rc = [&]() -> int {
@@ -800,7 +808,7 @@ static bool want_tile_order(const par_ctx* c, int n_lights) {
     // 3840x2160 = 7 waves, a launch too many at 480x320 = 0.13 waves).
     int first, rows;
     owned_tile_rows(c->d, first, rows);
-    const long tiles = (long)rows * c->d.HW;
+    const long tiles = (long)rows * tiles_per_stripe(c->d);
     return n_lights == 1 && tiles >= c->cta_slots && tiles <= 3L * c->cta_slots;
 }
 
@@ -910,10 +918,18 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
             cudaStream_t cs = n_chunks > 1 ? c->copy_stream : c->stream;
             if (n_chunks > 1) PAR_CUDA(cudaStreamWaitEvent(cs, c->ev_chunk[k][1], 0));
             const size_t row_bytes = sizeof(par_color) * (size_t)d.W, pitch = host_pitch(c);
-            for (int t = first_owned, q = 0; q < (d.stripe_n == 1 ? 1 : n_owned); q++, t += d.stripe_n) {
+            const int seg = stripe_segments(d);
+            const size_t seg_bytes = row_bytes / (size_t)seg;  // bytes of a stripe's rows (the whole row unless stripe_s > 1)
+            for (int v = first_owned, q = 0; q < (d.stripe_n == 1 ? 1 : n_owned); q++, v += d.stripe_n) {
+                const int t = v / seg;
                 const int sa = d.stripe_n == 1 ? ra : std::max(t * kBin, ra), sb = d.stripe_n == 1 ? rb : std::min((t + 1) * kBin, rb);
                 if (sb <= sa) continue;
-                if (pitch == row_bytes)  // packed rows: a plain linear copy
+                if (seg > 1) {  // a stripe that is part of a tile row: its columns only
+                    const size_t col = (size_t)(v % seg) * seg_bytes;
+                    PAR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(host_out) + (size_t)sa * pitch + col, pitch,
+                                               reinterpret_cast<const char*>(d_out) + (size_t)sa * row_bytes + col, row_bytes,
+                                               seg_bytes, (size_t)(sb - sa), cudaMemcpyDeviceToHost, cs));
+                } else if (pitch == row_bytes)  // packed rows: a plain linear copy
                     PAR_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host_out) + (size_t)sa * pitch,
                                              reinterpret_cast<const char*>(d_out) + (size_t)sa * row_bytes,
                                              row_bytes * (size_t)(sb - sa), cudaMemcpyDeviceToHost, cs));
@@ -958,8 +974,9 @@ size_t par_staging_bytes(const par_ctx* c) {
 
 int par_render_device_striped(par_ctx* c, const par_light* lights, int n_lights, void* d_staging) {
     if (!c || !d_staging) return fail(PAR_ERR_INVALID_ARG, "par_render_device_striped: null argument%s%s");
-    if (c->d.row0 != 0 || c->d.row1 != c->d.H)
-        return fail(PAR_ERR_INVALID_ARG, "par_render_device_striped: the context must cover the whole frame%s%s");
+    if (c->d.row0 != 0 || c->d.row1 != c->d.H || c->d.stripe_s > 1)
+        return fail(PAR_ERR_INVALID_ARG,
+                    "par_render_device_striped: the context must cover the whole frame with whole-row stripes (stripe_split <= 1)%s%s");
     return render_impl(c, lights, n_lights, static_cast<uchar4*>(d_staging), nullptr, true);
 }
 
@@ -1233,7 +1250,8 @@ static int enqueue_owned_rows_d2h(par_ctx* c, const uchar4* d_src, par_color* ho
     if (count <= 0) return PAR_OK;
     const int n = d.stripe_n > 1 ? d.stripe_n : 1;
     const int last = first + (count - 1) * n;
-    const bool whole_tiles = first * kBin >= d.row0 && (last + 1) * kBin <= d.row1;
+    const int seg = stripe_segments(d);
+    const bool whole_tiles = (first / seg) * kBin >= d.row0 && (last / seg + 1) * kBin <= d.row1;
     char* dst = reinterpret_cast<char*>(host_frame);
     const char* src = reinterpret_cast<const char*>(d_src);
     if (n == 1) {  // a band (or the whole frame): one block of rows — a plain linear copy when the rows are packed
@@ -1243,6 +1261,31 @@ static int enqueue_owned_rows_d2h(par_ctx* c, const uchar4* d_src, par_color* ho
         else
             PAR_CUDA(cudaMemcpy2DAsync(dst + d.row0 * pitch, pitch, src + d.row0 * row_bytes, row_bytes, row_bytes,
                                        (size_t)(d.row1 - d.row0), cudaMemcpyDeviceToHost, st));
+        return PAR_OK;
+    }
+    if (seg > 1) {  // stripes that are parts of tile rows: one 2-D copy each (its columns of its 40 rows)
+        const size_t seg_bytes = row_bytes / (size_t)seg;
+        if (whole_tiles && n % seg == 0) {
+            // the rank's stripes are the same columns of every (n / seg)-th tile row: ONE 3-D DMA
+            // (x = the stripe's bytes of a row, y = 40 rows, z = the stripes, a slice = n / seg tile rows)
+            const size_t slice_rows = (size_t)kBin * (size_t)(n / seg);
+            const size_t col = (size_t)(first % seg) * seg_bytes, r0 = (size_t)(first / seg) * kBin;
+            cudaMemcpy3DParms p3 = {};
+            p3.srcPtr = make_cudaPitchedPtr(const_cast<char*>(src) + r0 * row_bytes + col, row_bytes, row_bytes, slice_rows);
+            p3.dstPtr = make_cudaPitchedPtr(dst + r0 * pitch + col, pitch, row_bytes, slice_rows);
+            p3.extent = make_cudaExtent(seg_bytes, kBin, (size_t)count);
+            p3.kind = cudaMemcpyDeviceToHost;
+            PAR_CUDA(cudaMemcpy3DAsync(&p3, st));
+            return PAR_OK;
+        }
+        for (int v = first; v <= last; v += n) {
+            const int t = v / seg;
+            const int r0 = std::max(t * kBin, d.row0), r1 = std::min((t + 1) * kBin, d.row1);
+            if (r1 <= r0) continue;
+            const size_t col = (size_t)(v % seg) * seg_bytes;
+            PAR_CUDA(cudaMemcpy2DAsync(dst + r0 * pitch + col, pitch, src + r0 * row_bytes + col, row_bytes, seg_bytes,
+                                       (size_t)(r1 - r0), cudaMemcpyDeviceToHost, st));
+        }
         return PAR_OK;
     }
     if (whole_tiles && pitch == row_bytes) {  // the owned stripes lie at a regular pitch: one strided DMA
@@ -1399,7 +1442,7 @@ int par_wait_frame(par_ctx* c, par_stats* stats) {
         stats->n_entities = c->n_entities;
         stats->n_survivors = lc.n_survivors;
         stats->n_inserts = lc.n_inserts;
-        stats->rays = owned_row_count(c) * c->d.W * (1 + (uint64_t)c->slot_lights[slot]);
+        stats->rays = owned_pixel_count(c) * (1 + (uint64_t)c->slot_lights[slot]);
     }
     return lc.bad_scene ? bad_scene_error(lc) : PAR_OK;
 }
@@ -1414,7 +1457,8 @@ int par_set_cursor(par_ctx* c, int x, int y) {
     }
     const ViewDims& d = c->d;
     const int n = d.stripe_n > 1 ? d.stripe_n : 1;
-    if (x >= d.W || y < d.row0 || y >= d.row1 || (y / kBin) % n != (n > 1 ? d.stripe_i : 0))
+    const int stripe_of_pixel = (y / kBin) * stripe_segments(d) + (x / kBin) / tiles_per_stripe(d);
+    if (x >= d.W || y < d.row0 || y >= d.row1 || stripe_of_pixel % n != (n > 1 ? d.stripe_i : 0))
         return fail(PAR_ERR_INVALID_ARG, "par_set_cursor: the pixel is not one this context renders%s%s");
     c->cursor_x = x;
     c->cursor_y = y;
@@ -1530,7 +1574,7 @@ int par_get_stats(par_ctx* c, par_stats* st) {
     st->n_entities = c->n_entities;
     st->n_survivors = c->h_ctr->n_survivors;
     st->n_inserts = c->h_ctr->n_inserts;
-    st->rays = owned_row_count(c) * c->d.W * (1 + (uint64_t)c->last_n_lights);
+    st->rays = owned_pixel_count(c) * (1 + (uint64_t)c->last_n_lights);
     return PAR_OK;
 }
 

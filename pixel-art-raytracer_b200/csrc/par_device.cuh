@@ -28,13 +28,21 @@ struct ViewDims {
     int HW, HH, HL;  // hash_width / hash_height / hash_length (alternative.cpp:120-122)
     int V;           // hash_volume
     int row0, row1;  // band rendered by this context
-    int stripe_n;    // >= 1: only tile rows t with t % stripe_n == stripe_i are rendered
+    int stripe_n;    // >= 1: only the stripes v with v % stripe_n == stripe_i are rendered
     int stripe_i;    //       (40-row stripes interleaved over ranks: load balance)
+    int stripe_s;    // >= 1: a tile row is cut into stripe_s stripes of HW / stripe_s tiles each; stripe
+                     //       v = tile row * stripe_s + segment (equal stripe counts per rank when HH % ranks != 0)
 };
 
-// Tile rows [first, first + count*stripe_n) step stripe_n owned by this context within its band.
+// Stripe v -> its tile row, and the tiles per stripe.
+__host__ __device__ __forceinline__ int stripe_segments(const ViewDims& d) { return d.stripe_s > 1 ? d.stripe_s : 1; }
+__host__ __device__ __forceinline__ int tiles_per_stripe(const ViewDims& d) { return d.HW / stripe_segments(d); }
+
+// Stripes first, first + stripe_n, ... (count of them) owned by this context within its band.  With stripe_s == 1 a
+// stripe IS a tile row.
 __host__ __device__ __forceinline__ void owned_tile_rows(const ViewDims& d, int& first, int& count) {
-    const int t0 = d.row0 / kBin, t1 = (d.row1 + kBin - 1) / kBin;  // band's tile rows [t0, t1)
+    const int seg = stripe_segments(d);
+    const int t0 = (d.row0 / kBin) * seg, t1 = ((d.row1 + kBin - 1) / kBin) * seg;  // band's stripes [t0, t1)
     const int n = d.stripe_n > 1 ? d.stripe_n : 1, i = d.stripe_n > 1 ? d.stripe_i : 0;
     first = t0 + ((i - t0) % n + n) % n;
     count = first < t1 ? (t1 - first + n - 1) / n : 0;

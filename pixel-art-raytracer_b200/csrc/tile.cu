@@ -265,8 +265,10 @@ k_tile(const __grid_constant__ TileParams p) {
     const int tid = threadIdx.x, lane = tid & 31;
     const long long t_begin = p.tile_cost ? clock64() : 0;
     const int slot = p.tile_order ? p.tile_order[blockIdx.x] : (int)blockIdx.x;
-    const int bx = slot % d.HW;
-    const int ty = p.tile_row_first + (slot / d.HW) * max(d.stripe_n, 1);
+    const int tps = tiles_per_stripe(d);
+    const int stripe = p.tile_row_first + (slot / tps) * max(d.stripe_n, 1);  // (a stripe is a tile row unless stripe_s > 1)
+    const int ty = stripe / stripe_segments(d);
+    const int bx = (stripe % stripe_segments(d)) * tps + slot % tps;
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
     const int n_lights = p.n_lights;
     // The thread's pixels: rows rsub + 4m of column col.  A warp covers 8 adjacent columns (x 4 row
@@ -1126,10 +1128,11 @@ cudaError_t launch_tile(const TileParams& p, cudaStream_t st) {
     int first, tile_rows;
     owned_tile_rows(p.d, first, tile_rows);
     if (tile_rows <= 0) return cudaSuccess;
+    const int n_tiles = tile_rows * tiles_per_stripe(p.d);  // (tile_rows counts stripes)
     if (p.gbuf || p.gbuf_only || p.dbg_t || p.dbg_factor || p.phase_cycles)
-        k_tile<true><<<tile_rows * p.d.HW, kT, sizeof(TileSmem), st>>>(p);
+        k_tile<true><<<n_tiles, kT, sizeof(TileSmem), st>>>(p);
     else
-        k_tile<false><<<tile_rows * p.d.HW, kT, sizeof(TileSmem), st>>>(p);
+        k_tile<false><<<n_tiles, kT, sizeof(TileSmem), st>>>(p);
     return cudaGetLastError();
 }
 
@@ -1145,19 +1148,24 @@ k_tile_order(const unsigned* __restrict__ cost, int* __restrict__ order, ViewDim
     constexpr int kBuckets = 256;
     __shared__ unsigned s_max;
     __shared__ int s_hist[kBuckets], s_base[kBuckets];
-    const int n = tile_rows * d.HW, tid = threadIdx.x;
+    const int tps = tiles_per_stripe(d), seg = stripe_segments(d);
+    const int n = tile_rows * tps, tid = threadIdx.x;
     const int stripe = max(d.stripe_n, 1);
+    auto cost_of = [&](int t) {  // owned tile t (the CTA slot numbering of k_tile) -> its cost
+        const int v = tile_row_first + (t / tps) * stripe;
+        return cost[(v / seg) * d.HW + (v % seg) * tps + t % tps];
+    };
     if (tid == 0) s_max = 1u;
     if (tid < kBuckets) s_hist[tid] = 0;
     __syncthreads();
     unsigned mx = 0u;
-    for (int t = tid; t < n; t += blockDim.x) mx = max(mx, cost[(tile_row_first + (t / d.HW) * stripe) * d.HW + t % d.HW]);
+    for (int t = tid; t < n; t += blockDim.x) mx = max(mx, cost_of(t));
     mx = __reduce_max_sync(0xffffffffu, mx);
     if ((tid & 31) == 0) atomicMax(&s_max, mx);
     __syncthreads();
     const float scale = (float)(kBuckets - 1) / (float)s_max;
     auto bucket = [&](int t) {  // bucket 0 = most expensive
-        const unsigned c = cost[(tile_row_first + (t / d.HW) * stripe) * d.HW + t % d.HW];
+        const unsigned c = cost_of(t);
         return (kBuckets - 1) - min(kBuckets - 1, (int)((float)c * scale));
     };
     for (int t = tid; t < n; t += blockDim.x) atomicAdd(&s_hist[bucket(t)], 1);

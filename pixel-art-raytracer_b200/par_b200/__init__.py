@@ -53,7 +53,7 @@ class Config(C.Structure):
     _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("length", C.c_int32),
                 ("device", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
                 ("ambient", C.c_float), ("stripe_count", C.c_int32), ("stripe_index", C.c_int32),
-                ("tile_order", C.c_int32), ("reserved", C.c_int32 * 2)]
+                ("tile_order", C.c_int32), ("stripe_split", C.c_int32), ("reserved", C.c_int32)]
 
 
 class Stats(C.Structure):
@@ -274,10 +274,10 @@ class Renderer:
     """
 
     def __init__(self, W, H, L, device=0, row_begin=0, row_end=0, ambient=0.0, stripe_count=0,
-                 stripe_index=0, tile_order=0):
+                 stripe_index=0, tile_order=0, stripe_split=0):
         self.W, self.H, self.L = W, H, L
         self._h = C.c_void_p()
-        cfg = Config(W, H, L, device, row_begin, row_end, ambient, stripe_count, stripe_index, tile_order)
+        cfg = Config(W, H, L, device, row_begin, row_end, ambient, stripe_count, stripe_index, tile_order, stripe_split)
         self.row_begin = row_begin
         self.row_end = row_end if (row_begin or row_end) else H
         _check(lib().par_create(C.byref(self._h), C.byref(cfg)))

@@ -44,6 +44,30 @@ def owned_rows(H: int, world: int, rank: int) -> list[tuple[int, int]]:
     return [(t * 40, t * 40 + 40) for t in range(rank, H // 40, world)]
 
 
+def stripe_split_for(W: int, H: int, world: int) -> int:
+    """par_config.stripe_split that gives every rank the same number of stripes: the smallest s in
+    (1, 2, 4, 8) dividing W / 40 with (H / 40 * s) % world == 0 — e.g. 2 for the 108 tile rows of a
+    7680x4320 frame on 8 GPUs; 1 (whole tile rows) when there is none or the rows already divide."""
+    tile_rows, tile_cols = H // 40, W // 40
+    if world <= 1 or tile_rows % world == 0:
+        return 1
+    for s in (2, 4, 8):
+        if tile_cols % s == 0 and (tile_rows * s) % world == 0:
+            return s
+    return 1
+
+
+def owned_rects(W: int, H: int, world: int, rank: int, split: int = 1) -> list[tuple[int, int, int, int]]:
+    """(row0, row1, col0, col1) of the stripes rank `rank` renders with par_config.stripe_split = split."""
+    split = max(split, 1)
+    cols = (W // 40 // split) * 40
+    out = []
+    for v in range(rank, (H // 40) * split, world):
+        t, seg = divmod(v, split)
+        out.append((t * 40, t * 40 + 40, seg * cols, (seg + 1) * cols if split > 1 else W))
+    return out
+
+
 def gather_stripes(staging, world: int, rank: int, group=None) -> None:
     """staging: flat uint8 tensor [world][T][40*W*4] whose block `rank` is valid; in-place all-gather."""
     if world == 1:

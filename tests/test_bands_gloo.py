@@ -81,3 +81,28 @@ def test_band_rows():
     assert band_rows(4320, 1, 0) == (0, 4320)
     with pytest.raises(ValueError):
         band_rows(320, 2, 2)
+
+
+@pytest.mark.parametrize("W,H", [(3840, 2160), (7680, 4320), (1920, 1080), (640, 360), (480, 320)])
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_split_stripes_partition(W, H, world):
+    """par_config.stripe_split as bench.py picks it: the ranks' stripes tile the frame exactly once and,
+    whenever a split that evens the counts exists, every rank owns the same number of pixels."""
+    sys.path.insert(0, PKG)
+    from par_b200.bands import owned_rects, owned_rows, stripe_split_for
+    s = stripe_split_for(W, H, world)
+    assert s in (1, 2, 4, 8) and (W // 40) % s == 0
+    cover = np.zeros((H, W), np.int32)
+    px = []
+    for r in range(world):
+        rects = owned_rects(W, H, world, r, s)
+        for r0, r1, c0, c1 in rects:
+            cover[r0:r1, c0:c1] += 1
+        px.append(sum((r1 - r0) * (c1 - c0) for r0, r1, c0, c1 in rects))
+        if s == 1:
+            assert [(a, b) for a, b, _, _ in rects] == owned_rows(H, world, r)
+    assert (cover == 1).all()
+    if (H // 40 * s) % world == 0:
+        assert len(set(px)) == 1
+    if (W, H, world) == (7680, 4320, 8):
+        assert s == 2 and px[0] == W * H // 8

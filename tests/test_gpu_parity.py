@@ -434,6 +434,92 @@ def test_stripes_reassemble(par, n):
     assert np.array_equal(unstripe(staging, W, H, n).cpu().numpy(), full.view(np.uint8).reshape(-1))
 
 
+@pytest.mark.parametrize("n,split,band", [(2, 2, None), (4, 2, None), (8, 4, None), (3, 2, None), (8, 2, (55, 301))])
+def test_split_stripes_reassemble(par, n, split, band):
+    """stripe_split: a tile row is cut into `split` stripes of equal width and stripe v = tile row * split +
+    segment goes to rank v % n (equal stripe counts per rank when height / 40 is not a multiple of the rank
+    count: 9 tile rows here).  Every form of output a striped context has — the blocking par_render into a
+    host frame, par_read_stripes and the pipelined par_submit_frame into ONE shared host frame, and the fused
+    peer stores of par_render_device_peers (all contexts on this one device) — reassembles the one-context
+    frame; the stripe-major staging calls refuse such a context."""
+    W, H, L = 640, 360, 360
+    boxes, lights = par.scene_synthetic(W, H, L, n=1500, n_lights=5)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        full, _ = r.render(lights)
+    a, b = band or (0, H)
+    tps = W // 40 // split
+    own = []  # per rank: the pixels it owns
+    for i in range(n):
+        m = np.zeros((H, W), bool)
+        for v in range(i, (H // 40) * split, n):
+            t, sgm = divmod(v, split)
+            m[t * 40:t * 40 + 40, sgm * tps * 40:(sgm + 1) * tps * 40] = True
+        m[:a] = False
+        m[b:] = False
+        own.append(m)
+    assert sum(int(m.sum()) for m in own) == (b - a) * W
+    if band is None and (H // 40 * split) % n == 0:
+        assert len({int(m.sum()) for m in own}) == 1  # the point of the split: equal shares
+    kw = dict(row_begin=a, row_end=b) if band else {}
+    rens = [par.Renderer(W, H, L, stripe_count=n, stripe_index=i, stripe_split=split, **kw) for i in range(n)]
+    try:
+        out = np.zeros((H, W), par.COLOR)
+        shared = par.pinned_empty((H, W), par.COLOR)
+        piped = par.pinned_empty((H, W), par.COLOR)
+        h_boxes = par.pinned_empty(len(boxes), par.AABB)
+        h_boxes[:] = boxes
+        _u32(shared)[:] = 0xDEADBEEF
+        _u32(piped)[:] = 0xDEADBEEF
+        rays = 0
+        for i, r in enumerate(rens):
+            r.set_atlas()
+            r.set_scene(boxes)
+            part = np.zeros((H, W), par.COLOR)
+            _, st = r.render(lights, out=part)
+            rays += st["rays"]
+            assert not _u32(part)[~own[i]].any()
+            out[own[i]] = part[own[i]]
+            r.read_stripes(shared)
+            r.sync()
+            with pytest.raises(par.ParError):
+                r.render_device_striped(lights, 1)
+            # cursor: only on a pixel the context renders
+            ys, xs = np.nonzero(own[i])
+            r.set_cursor(int(xs[0]), int(ys[0]))
+            other = np.nonzero(~own[i])
+            with pytest.raises(par.ParError):
+                r.set_cursor(int(other[1][0]), int(other[0][0]))
+        assert rays == (b - a) * W * 6
+        assert np.array_equal(_u32(out[a:b]), _u32(full[a:b]))
+        assert np.array_equal(_u32(shared[a:b]), _u32(full[a:b]))
+        assert (_u32(shared[:a]) == 0xDEADBEEF).all() and (_u32(shared[b:]) == 0xDEADBEEF).all()
+        for r in rens:
+            r.submit_frame(h_boxes, lights, piped)
+        for r in rens:
+            r.wait_frame()
+        assert np.array_equal(_u32(piped[a:b]), _u32(full[a:b]))
+        assert (_u32(piped[:a]) == 0xDEADBEEF).all() and (_u32(piped[b:]) == 0xDEADBEEF).all()
+        if band is None:
+            # fused frame exchange: every context stores its tiles into every other context's frame too
+            for i, r in enumerate(rens):
+                for j, q in enumerate(rens):
+                    if i != j:
+                        r.peer_set(j, q.device_frame())
+            for r in rens:
+                r.render_device_peers(lights)
+            for r in rens:
+                r.sync()
+            for i, r in enumerate(rens):
+                got = r.read_frame()
+                r.sync()
+                assert np.array_equal(_u32(got), _u32(full)), f"context {i}"
+    finally:
+        for r in rens:
+            r.close()
+
+
 @pytest.mark.parametrize("n,band", [(1, None), (2, None), (3, None), (8, None), (1, (97, 333)), (3, (50, 430))])
 def test_read_stripes_into_one_host_frame(par, n, band):
     """par_read_stripes: every context copies only the rows it owns into ONE shared host frame
