@@ -222,7 +222,7 @@ class Job:
     """One workload on this rank's GPU: a striped context (tile row t -> rank t % N), the frame exchange
     of par_render_resident at N > 1, and the timing loop of the device-resident step."""
 
-    def __init__(self, env, name, exchange):
+    def __init__(self, env, name, exchange, want_sha=None):
         import numpy as np
         import torch
         import torch.distributed as dist
@@ -232,9 +232,30 @@ class Job:
         self.W, self.H, self.L, self.desc, self.boxes, self.lights = make_workload(par, name)
         self.rays_frame = self.W * self.H * (1 + len(self.lights))
         # equal stripe counts per rank (e.g. 108 tile rows over 8 GPUs: half tile rows); the NCCL fallback's
-        # stripe-major staging needs whole tile rows
+        # stripe-major staging needs whole tile rows.  PAR_BENCH_STRIPE_SPLIT overrides the choice.
         from par_b200.bands import stripe_split_for
-        self.split = 1 if exchange == "nccl" else stripe_split_for(self.W, self.H, world)
+        forced = os.environ.get("PAR_BENCH_STRIPE_SPLIT")
+        self.split = 1 if exchange == "nccl" or world == 1 else \
+            (max(1, int(forced)) if forced else stripe_split_for(self.W, self.H, world))
+        self.h_boxes = par.pinned_empty(len(self.boxes), par.AABB)
+        self.h_boxes[:] = self.boxes
+        self.np = np
+        self.split_fallback = None
+        self._build(exchange)
+        if self.split > 1 and not self._split_frames_ok(want_sha):
+            # never observed; the partition is new this round and a driver run must not die of it
+            self.split_fallback = f"stripe_split {self.split} gave a wrong or no frame at N = {world}; whole tile rows used"
+            if rank == 0:
+                print(f"bench.py: {self.split_fallback}", file=sys.stderr)
+            self.close()
+            self.split = 1
+            self._build(exchange)
+
+    def _build(self, exchange):
+        import torch
+        import torch.distributed as dist
+        env, par = self.env, self.par
+        world, rank, local, dev = env["world"], env["rank"], env["local"], env["dev"]
 
         def make_renderer():
             ren = par.Renderer(self.W, self.H, self.L, device=local, stripe_count=world, stripe_index=rank,
@@ -244,8 +265,6 @@ class Job:
             return ren
 
         self.ren = make_renderer()
-        self.h_boxes = par.pinned_empty(len(self.boxes), par.AABB)
-        self.h_boxes[:] = self.boxes
         self.exchange = "none" if world == 1 else exchange
         self.staging = self.frame = None
         if world > 1 and self.exchange in ("peer", "root"):
@@ -277,7 +296,39 @@ class Job:
         with torch.cuda.stream(env["stream"]):
             self.ren.set_scene(self.h_boxes)
         self.ren.sync()
-        self.np = np
+
+    def _split_frames_ok(self, want_sha):
+        """Two resident frames with the split partition, compared with the committed oracle frame on every rank
+        that holds a whole frame; False on any rank -> False on all (no host collective inside the try)."""
+        import torch
+        import torch.distributed as dist
+        env = self.env
+        try:
+            with torch.cuda.stream(env["stream"]):
+                for _ in range(2):
+                    self.step_resident()
+            torch.cuda.synchronize(env["dev"])
+            good = True
+            if want_sha and (env["rank"] == 0 or self.exchange in ("peer", "nccl")):
+                good = self.device_frame_sha() == want_sha
+            # the host-side form of the same partition (e2e: every rank DMAs its own stripes into one host frame)
+            from par_b200.bands import owned_rects
+            par = self.par
+            with par.Renderer(self.W, self.H, self.L, device=env["local"]) as one:
+                one.set_atlas()
+                one.set_scene(self.boxes)
+                full, _ = one.render(self.lights)
+            part = par.pinned_empty((self.H, self.W), par.COLOR)
+            self.ren.read_stripes(part)
+            self.ren.sync()
+            for r0, r1, c0, c1 in owned_rects(self.W, self.H, env["world"], env["rank"], self.split):
+                good = good and self.np.array_equal(part[r0:r1, c0:c1], full[r0:r1, c0:c1])
+        except Exception as e:
+            print(f"bench.py rank {env['rank']}: split check failed: {e}", file=sys.stderr)
+            good = False
+        ok = torch.tensor([1 if good else 0], dtype=torch.int32, device=env["dev"])
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        return int(ok.item()) == 1
 
     def step_resident(self):
         if self.exchange == "nccl":  # stripe-major staging + in-place NCCL all-gather + un-stripe
@@ -364,7 +415,7 @@ def series_other(env, args, ops_tab, name):
     """The device-resident step of another BASELINE.json workload (configs[2]: c3; configs[4]: c5b / c5) at this N."""
     import torch
     import torch.distributed as dist
-    job = Job(env, name, args.exchange)
+    job = Job(env, name, args.exchange, (ops_tab.get(name) or {}).get("frame_sha256"))
     steps = max(3, min(args.steps, args.steps_8k))
     with torch.cuda.stream(env["stream"]):
         for _ in range(3):                       # first frames: graph capture + tile costs for the CTA order
@@ -389,6 +440,7 @@ def series_other(env, args, ops_tab, name):
                "frames_per_s": round(1e3 * steps / ms, 2),
                "render_kernel_ms_per_rank": k, "render_kernel_ms_min": min(k), "render_kernel_ms_max": max(k),
                "scene_loader_ms": ranks[0]["scene_loader_ms"], "exchange": job.exchange, "stripe_split": job.split,
+               "stripe_split_fallback": job.split_fallback,
                "frame_check": {"oracle_frame_sha256": want,
                                "device_frames_equal_oracle": [r["frame_sha256"] == want for r in ranks
                                                               if r["frame_sha256"] is not None]}}
@@ -502,7 +554,7 @@ def ours(args):
     flush = env["flush"]
     ops_tab = load_json(os.path.join(ROOT, "tests", "golden", "workload_ops.json"), {}) or {}
 
-    job = Job(env, args.workload, args.exchange)
+    job = Job(env, args.workload, args.exchange, (ops_tab.get(args.workload) or {}).get("frame_sha256"))
     ren, W, H, L, lights, boxes, h_boxes = job.ren, job.W, job.H, job.L, job.lights, job.boxes, job.h_boxes
     n_lights, rays_frame, exchange = len(lights), job.rays_frame, job.exchange
     from par_b200.bands import owned_rects
@@ -751,6 +803,7 @@ def ours(args):
         "data": "synthetic",
         "config": {"workload": f"{args.workload}: {job.desc}", "view": [W, H, L], "n_entities": int(len(boxes)),
                    "n_lights": int(n_lights), "rays_per_frame": rays_frame, "stripe_split": job.split,
+                   "stripe_split_fallback": job.split_fallback,
                    "parallelism": ("1 GPU" if world == 1 else
                                    f"interleaved 40-row stripes x{world}, frame exchange fused into the render kernel "
                                    "(peer-memory stores over NVLink, arrival/credit flags in the frame footers, no "

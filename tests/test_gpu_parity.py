@@ -1262,3 +1262,58 @@ def test_many_groups_and_long_columns(par, oracle):
     lights["x"], lights["y"], lights["z"] = [100, 10, 190], [800, 300, 1500], [500, 2500, 100]
     got, ref = _render_both(par, oracle, W, H, L, boxes, lights)
     _assert_frame_equal(got, ref)
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("root,split", [(-1, 1), (0, 1), (-1, 2), (0, 2), (1, 2)])
+def test_resident_flag_exchange_two_contexts_one_device(par, root, split):
+    """The multi-GPU step of bench.py (par_exchange_setup + par_render_resident: the render kernels store
+    their stripes into the consumers' frames, arrival / credit flags in the frame footers order the frames,
+    the whole step one replayed CUDA graph) with both ranks' contexts on ONE device, so that a 1-GPU box
+    exercises it too: whole tile rows and stripe_split = 2 over an odd number of tile rows (17), all-gather
+    and gather-to-root.  Replayed frames, frames after a light change (re-captured graphs) and after an entity
+    update must leave the one-context frame on every consumer."""
+    W, H, L = 1280, 680, 680
+    boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
+    kw = dict(stripe_split=split) if split > 1 else {}
+    with par.Renderer(W, H, L) as ref, \
+            par.Renderer(W, H, L, stripe_count=2, stripe_index=0, **kw) as a, \
+            par.Renderer(W, H, L, stripe_count=2, stripe_index=1, **kw) as b:
+        ref.set_atlas()
+        a.peer_set(1, b.device_frame())
+        b.peer_set(0, a.device_frame())
+        for r in (a, b):
+            r.set_atlas()
+            r.set_scene(boxes)
+            r.exchange_setup(root)
+
+        def check(tag):
+            ref.set_scene(boxes)
+            want, _ = ref.render(lights)
+            for r in (a, b):
+                r.sync()
+            for idx, r in enumerate((a, b)):
+                if root in (-1, idx):
+                    got = r.read_frame()
+                    r.sync()
+                    assert np.array_equal(_u32(want), _u32(got)), f"{tag}: rank {idx}"
+
+        for _ in range(7):  # first frames run plainly / are captured, the later ones are graph replays
+            a.render_resident(lights)
+            b.render_resident(lights)
+        check("replayed frames")
+        lights = lights.copy()
+        lights["x"] += 35
+        lights["z"] += 20
+        for _ in range(3):
+            b.render_resident(lights)  # the enqueue order between the ranks must not matter
+            a.render_resident(lights)
+        check("after moving the lights")
+        boxes = boxes.copy()
+        boxes["px"][:4] += 60
+        for r in (a, b):
+            r.update_entities(0, boxes[:4])
+        for _ in range(2):
+            a.render_resident(lights)
+            b.render_resident(lights)
+        check("after an entity update")
