@@ -202,8 +202,8 @@ def test_headless_driver_writes_the_frame_sequence(par, golden, tmp_path):
     assert len(seen) == n  # the player moves every frame
 
 
-@pytest.mark.parametrize("root", [-1, 0, 1])
-def test_resident_frames_with_flag_exchange(par, root):
+@pytest.mark.parametrize("root,split", [(-1, 1), (0, 1), (1, 1), (-1, 2), (0, 4)])
+def test_resident_frames_with_flag_exchange(par, root, split):
     """par_render_resident + par_exchange_setup on two GPUs: the render kernels store their stripes into the
     consumers' frames, arrival / credit flags in the frame footers order the frames (no collective, no host
     round trip).  Frames replayed from the captured graphs, frames after a light change (graphs re-captured)
@@ -213,8 +213,8 @@ def test_resident_frames_with_flag_exchange(par, root):
     W, H, L = 1280, 720, 720
     boxes, lights = par.scene_synthetic(W, H, L, n=3000, n_lights=6)
     with par.Renderer(W, H, L) as ref, \
-            par.Renderer(W, H, L, device=0, stripe_count=2, stripe_index=0) as a, \
-            par.Renderer(W, H, L, device=1, stripe_count=2, stripe_index=1) as b:
+            par.Renderer(W, H, L, device=0, stripe_count=2, stripe_index=0, stripe_split=split) as a, \
+            par.Renderer(W, H, L, device=1, stripe_count=2, stripe_index=1, stripe_split=split) as b:
         ref.set_atlas()
         a.peer_set(1, b.device_frame())
         b.peer_set(0, a.device_frame())
