@@ -1,9 +1,8 @@
 #!/usr/bin/env bash
 # Developer helper for a 2-GPU box (gpurun --gpus 2): the multi-GPU parity tests, then bench.py at N = 2 with
-# whole tile rows and with a forced stripe_split of 2 (A/B of the split partition where it is not needed).
+# a forced stripe_split of 2 (the split partition on real peers, where whole rows would do).
 mkdir -p gpurun_out
 timeout 400 python -m pytest tests/test_gpu_multi.py -m gpu -x -q > gpurun_out/r02_n2_pytest.log 2>&1; echo "pytest rc=$?"
 tail -4 gpurun_out/r02_n2_pytest.log
-STEPS=50 EXTRA="--no-c4 --steps-8k 5" tools/scale_run.sh r02_n2_rows 2
 PAR_BENCH_STRIPE_SPLIT=2 STEPS=50 EXTRA="--no-c4 --steps-8k 5" tools/scale_run.sh r02_n2_split2 2
 tail -3 gpurun_out/r02_n2_*err_2.log
