@@ -770,7 +770,7 @@ def ours(args):
         roofline.update({"achieved": round(ex, 2), "frac": round(ex / peak_ops, 3),
                          "warp_instructions_per_launch": cap["warp_instructions"] * frac_rows,
                          "traffic": (cap["dram_bytes_read"] + cap["dram_bytes_write"]) if world == 1 else None,
-                         "ncu": {k: cap.get(k) for k in ("issue_active_pct", "warps_active_pct", "duration_us_under_ncu",
+                         "ncu": {k: cap.get(k) for k in ("kernel", "issue_active_pct", "warps_active_pct", "duration_us_under_ncu",
                                                          "registers_per_thread", "source")},
                          "note": "frac = executed warp instructions (ncu smsp__inst_executed.sum, capture of this very "
                                  "build: source hash matches) x 32 lanes / live CUDA-event kernel time / peak = the "

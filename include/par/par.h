@@ -97,9 +97,11 @@ typedef struct par_config {
                           /* 0 = automatic (>= 2 lights, or one light when the tiles make 1-3 waves */
                           /* of resident CTAs), 1 = always, -1 = never                              */
     int32_t stripe_split; /* > 1: every 40-row tile row is cut into this many stripes of equal width  */
-                          /* (must divide width / 40) and stripe v = tile row * split + segment goes to */
-                          /* rank v % stripe_count: equal stripe counts per rank when height / 40 is not */
-                          /* a multiple of the rank count (e.g. 108 tile rows over 8 GPUs: split 2).     */
+                          /* (must divide width / 40) and stripe v = tile row * split + k goes to rank   */
+                          /* v % stripe_count: equal stripe counts per rank when height / 40 is not a    */
+                          /* multiple of the rank count (e.g. 108 tile rows over 8 GPUs: split 2).  Its  */
+                          /* columns are segment (k + v / lcm(stripe_count, split)) % split of the row,  */
+                          /* so a rank's stripes take every column segment in turn.                      */
                           /* 0 / 1 = whole tile rows.  Not with the stripe-major staging calls.          */
     int32_t reserved;
 } par_config;

@@ -3,6 +3,7 @@
 // loop body /root/reference/src/alternative.cpp:689-760.  No compute happens on the host and
 // there is no CPU fallback: without a CUDA device every entry point fails.
 #include <algorithm>
+#include <numeric>
 #include <climits>
 #include <cstdio>
 #include <cstdlib>
@@ -391,6 +392,7 @@ int par_create(par_ctx** out, const par_config* cfg) {
     d.stripe_n = cfg->stripe_count > 1 ? cfg->stripe_count : 1;
     d.stripe_i = cfg->stripe_count > 1 ? cfg->stripe_index : 0;
     d.stripe_s = split;
+    d.stripe_rot = std::lcm(d.stripe_n, split);
 
     DeviceGuard guard(cfg->device);
     int rc = [&]() -> int {
@@ -775,6 +777,18 @@ int par_update_entities(par_ctx* c, int first, int count, const par_aabb* aabbs,
 }
 
 // ---- frame ---------------------------------------------------------------------------------------------
+// Which build of the render kernel a frame runs on (tile.cu): the one-light configuration (6 CTAs per SM, small
+// lists) for one-light frames of at least 4 waves of CTAs — below that the longer latency of a CTA with 64
+// registers costs more than the sixth CTA hides (1920x1080 = 1.75 waves: +1 %; 480x320: +8 %).
+// PAR_DEBUG_FLAGS 256: never, 512: always (the parity tests run many-light scenes on it).
+static bool want_one_light_config(const par_ctx* c, int n_lights) {
+    if (c->debug_flags & 256) return false;
+    if (c->debug_flags & 512) return true;
+    int first, rows;
+    owned_tile_rows(c->d, first, rows);
+    return n_lights == 1 && (long)rows * tiles_per_stripe(c->d) >= 4L * c->cta_slots;
+}
+
 static void fill_tile_params(par_ctx* c, TileParams& tp, const par_light* lights, int n_lights, uchar4* d_out) {
     const GridBuffers& g = c->gen[c->cur];
     memset(&tp, 0, sizeof tp);
@@ -792,6 +806,7 @@ static void fill_tile_params(par_ctx* c, TileParams& tp, const par_light* lights
     tp.ambient = c->ambient;
     tp.probe_x = tp.probe_y = -1;
     tp.debug_flags = c->debug_flags;
+    tp.one_light_config = want_one_light_config(c, n_lights);
     tp.phase_cycles = c->d_phase_cycles;  // NULL unless par_debug_phase_timing enabled it
     tp.dbg_light = -1;
     for (int l = 0; l < n_lights; l++)
@@ -925,7 +940,7 @@ static int render_impl(par_ctx* c, const par_light* lights, int n_lights, uchar4
                 const int sa = d.stripe_n == 1 ? ra : std::max(t * kBin, ra), sb = d.stripe_n == 1 ? rb : std::min((t + 1) * kBin, rb);
                 if (sb <= sa) continue;
                 if (seg > 1) {  // a stripe that is part of a tile row: its columns only
-                    const size_t col = (size_t)(v % seg) * seg_bytes;
+                    const size_t col = (size_t)stripe_column_segment(d, v) * seg_bytes;
                     PAR_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(host_out) + (size_t)sa * pitch + col, pitch,
                                                reinterpret_cast<const char*>(d_out) + (size_t)sa * row_bytes + col, row_bytes,
                                                seg_bytes, (size_t)(sb - sa), cudaMemcpyDeviceToHost, cs));
@@ -1266,23 +1281,28 @@ static int enqueue_owned_rows_d2h(par_ctx* c, const uchar4* d_src, par_color* ho
     if (seg > 1) {  // stripes that are parts of tile rows: one 2-D copy each (its columns of its 40 rows)
         const size_t seg_bytes = row_bytes / (size_t)seg;
         if (whole_tiles && n % seg == 0) {
-            // the rank's stripes are the same columns of every (n / seg)-th tile row: ONE 3-D DMA
-            // (x = the stripe's bytes of a row, y = 40 rows, z = the stripes, a slice = n / seg tile rows)
-            const size_t slice_rows = (size_t)kBin * (size_t)(n / seg);
-            const size_t col = (size_t)(first % seg) * seg_bytes, r0 = (size_t)(first / seg) * kBin;
-            cudaMemcpy3DParms p3 = {};
-            p3.srcPtr = make_cudaPitchedPtr(const_cast<char*>(src) + r0 * row_bytes + col, row_bytes, row_bytes, slice_rows);
-            p3.dstPtr = make_cudaPitchedPtr(dst + r0 * pitch + col, pitch, row_bytes, slice_rows);
-            p3.extent = make_cudaExtent(seg_bytes, kBin, (size_t)count);
-            p3.kind = cudaMemcpyDeviceToHost;
-            PAR_CUDA(cudaMemcpy3DAsync(&p3, st));
+            // the column segment of the rank's stripes advances by one per stripe (stripe_column_segment: the
+            // rotation every lcm(n, seg) = n stripes), so every seg-th of them has the same columns, n tile rows
+            // apart: seg 3-D DMAs (x = the stripe's bytes of a row, y = 40 rows, z = the stripes, a slice = n
+            // tile rows)
+            const size_t slice_rows = (size_t)kBin * (size_t)n;
+            for (int j = 0; j < seg && j < count; j++) {
+                const int v = first + j * n;
+                const size_t col = (size_t)stripe_column_segment(d, v) * seg_bytes, r0 = (size_t)(v / seg) * kBin;
+                cudaMemcpy3DParms p3 = {};
+                p3.srcPtr = make_cudaPitchedPtr(const_cast<char*>(src) + r0 * row_bytes + col, row_bytes, row_bytes, slice_rows);
+                p3.dstPtr = make_cudaPitchedPtr(dst + r0 * pitch + col, pitch, row_bytes, slice_rows);
+                p3.extent = make_cudaExtent(seg_bytes, kBin, (size_t)((count - j + seg - 1) / seg));
+                p3.kind = cudaMemcpyDeviceToHost;
+                PAR_CUDA(cudaMemcpy3DAsync(&p3, st));
+            }
             return PAR_OK;
         }
         for (int v = first; v <= last; v += n) {
             const int t = v / seg;
             const int r0 = std::max(t * kBin, d.row0), r1 = std::min((t + 1) * kBin, d.row1);
             if (r1 <= r0) continue;
-            const size_t col = (size_t)(v % seg) * seg_bytes;
+            const size_t col = (size_t)stripe_column_segment(d, v) * seg_bytes;
             PAR_CUDA(cudaMemcpy2DAsync(dst + r0 * pitch + col, pitch, src + r0 * row_bytes + col, row_bytes, seg_bytes,
                                        (size_t)(r1 - r0), cudaMemcpyDeviceToHost, st));
         }
@@ -1457,7 +1477,7 @@ int par_set_cursor(par_ctx* c, int x, int y) {
     }
     const ViewDims& d = c->d;
     const int n = d.stripe_n > 1 ? d.stripe_n : 1;
-    const int stripe_of_pixel = (y / kBin) * stripe_segments(d) + (x / kBin) / tiles_per_stripe(d);
+    const int stripe_of_pixel = stripe_of_segment(d, y / kBin, (x / kBin) / tiles_per_stripe(d));
     if (x >= d.W || y < d.row0 || y >= d.row1 || stripe_of_pixel % n != (n > 1 ? d.stripe_i : 0))
         return fail(PAR_ERR_INVALID_ARG, "par_set_cursor: the pixel is not one this context renders%s%s");
     c->cursor_x = x;

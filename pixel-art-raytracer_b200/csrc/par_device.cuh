@@ -32,11 +32,30 @@ struct ViewDims {
     int stripe_i;    //       (40-row stripes interleaved over ranks: load balance)
     int stripe_s;    // >= 1: a tile row is cut into stripe_s stripes of HW / stripe_s tiles each; stripe
                      //       v = tile row * stripe_s + segment (equal stripe counts per rank when HH % ranks != 0)
+    int stripe_rot;  // lcm(stripe_n, stripe_s): the stripes after which the column segments rotate by one (below)
 };
 
 // Stripe v -> its tile row, and the tiles per stripe.
 __host__ __device__ __forceinline__ int stripe_segments(const ViewDims& d) { return d.stripe_s > 1 ? d.stripe_s : 1; }
 __host__ __device__ __forceinline__ int tiles_per_stripe(const ViewDims& d) { return d.HW / stripe_segments(d); }
+
+// Column segment of stripe v within its tile row v / stripe_s: v % stripe_s rotated by one for every
+// lcm(ranks, stripe_s) stripes.  Without the rotation rank v % ranks would own the same columns in every one of
+// its tile rows whenever ranks and stripe_s have a common factor (2 stripes per row over 8 ranks: the even ranks
+// the left half of the image, the odd ranks the right half — measured 12 % apart on the 8K frames); with it a
+// rank's stripes visit all column segments in turn.  All stripes of a tile row share v / lcm (the lcm is a
+// multiple of stripe_s), so the segments of a row are permuted, never doubled.
+__host__ __device__ __forceinline__ int stripe_column_segment(const ViewDims& d, int v) {
+    const int s = stripe_segments(d);
+    return s > 1 ? (v % s + v / d.stripe_rot) % s : 0;
+}
+// ... and back: the stripe that holds column segment `seg` of tile row t.
+__host__ __device__ __forceinline__ int stripe_of_segment(const ViewDims& d, int t, int seg) {
+    const int s = stripe_segments(d);
+    if (s == 1) return t;
+    const int rot = (t * s / d.stripe_rot) % s;
+    return t * s + (seg - rot + s) % s;
+}
 
 // Stripes first, first + stripe_n, ... (count of them) owned by this context within its band.  With stripe_s == 1 a
 // stripe IS a tile row.

@@ -96,6 +96,7 @@ struct TileParams {
     int* probe_a;
     int* probe_b;
     int debug_flags;           // bit 0: disable the shaft cull (A/B measurements and tests only)
+    int one_light_config;      // 1: launch the 6-CTAs-per-SM build of the kernel (tile_one_light.cu; production frames only)
     unsigned long long* phase_cycles;  // optional debug instrumentation: 16 counters (NULL in production)
     int dbg_light;             // optional export of fp32 intermediates: t.xyz + Lambert term of this light
     float4* dbg_t;             //   [W*H]
@@ -106,6 +107,11 @@ size_t tile_smem_bytes();
 cudaError_t configure_tile();  // per device, before the first launch
 int tile_ctas_per_sm();        // resident CTAs of the production kernel per SM (after configure_tile)
 cudaError_t launch_tile(const TileParams& p, cudaStream_t s);
+// the second build of the same kernel for one-light frames (tile_one_light.cu); launch_tile dispatches to it
+size_t tile_one_light_smem_bytes();
+cudaError_t configure_tile_one_light();
+int tile_one_light_ctas_per_sm();  // 6 on sm_100; 0 = the query failed
+cudaError_t launch_tile_one_light(const TileParams& p, int n_tiles, cudaStream_t s);
 cudaError_t launch_tile_order(const unsigned* cost, int* order, const ViewDims& d, cudaStream_t s);
 
 }  // namespace par

@@ -50,6 +50,22 @@
 #include "par_kernels.cuh"
 #include "shaft.cuh"
 
+// This file is compiled twice.  On its own it gives the general configuration: 5 CTAs per SM (72 registers,
+// 44.6 KB of shared memory) with lists sized for many-light rounds.  Through tile_one_light.cu
+// (PAR_TILE_ONE_LIGHT) it gives the configuration for one-light frames of many CTA waves: 6 CTAs per SM (64
+// registers, 36.9 KB) with the smallest lists the phases allow — a one-light round holds a tile's few z-groups
+// only, and a sixth resident CTA covers more of the barrier and latency chain of the others' rounds (3840x2160
+// default scene: 0.248 -> 0.230 ms; 16 lights: 2.14 -> 2.56 ms, which is why it is not the only one).  Same
+// code, same results: rounds that overflow a list are re-walked in either (par_api.cu picks per frame).
+#ifdef PAR_TILE_ONE_LIGHT
+#define PAR_TILE_MIN_CTAS 6
+#define PAR_TILE_LIST_CAP 288
+#define PAR_TILE_HASH_BITS 9
+#define PAR_TILE_OCC_CAP 384
+#define PAR_TILE_ENTRY_CAP 176
+#define k_tile k_tile_one_light
+#endif
+
 namespace par {
 
 #ifndef PAR_TILE_MIN_CTAS
@@ -268,7 +284,7 @@ k_tile(const __grid_constant__ TileParams p) {
     const int tps = tiles_per_stripe(d);
     const int stripe = p.tile_row_first + (slot / tps) * max(d.stripe_n, 1);  // (a stripe is a tile row unless stripe_s > 1)
     const int ty = stripe / stripe_segments(d);
-    const int bx = (stripe % stripe_segments(d)) * tps + slot % tps;
+    const int bx = stripe_column_segment(d, stripe) * tps + slot % tps;
     const int ra = max(ty * kBin, d.row0), rb = min(ty * kBin + kBin, d.row1);
     const int n_lights = p.n_lights;
     // The thread's pixels: rows rsub + 4m of column col.  A warp covers 8 adjacent columns (x 4 row
@@ -1106,12 +1122,38 @@ k_tile(const __grid_constant__ TileParams p) {
     }
 }
 
+#ifdef PAR_TILE_ONE_LIGHT
+// ---- the one-light configuration (see the top of the file): production frames only ----
+size_t tile_one_light_smem_bytes() { return sizeof(TileSmem); }
+
+cudaError_t configure_tile_one_light() {
+    return cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+}
+
+int tile_one_light_ctas_per_sm() {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_tile<false>, kT, sizeof(TileSmem)) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    return n;
+}
+
+cudaError_t launch_tile_one_light(const TileParams& p, int n_tiles, cudaStream_t st) {
+    k_tile<false><<<n_tiles, kT, sizeof(TileSmem), st>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace par
+#else
 size_t tile_smem_bytes() { return sizeof(TileSmem); }
 
 cudaError_t configure_tile() {
     cudaError_t e = cudaFuncSetAttribute(k_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    e = cudaFuncSetAttribute(k_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    if (e != cudaSuccess) return e;
+    return configure_tile_one_light();
 }
 
 // CTAs of the production render kernel one SM holds at a time (occupancy query; 5 on sm_100).
@@ -1131,6 +1173,8 @@ cudaError_t launch_tile(const TileParams& p, cudaStream_t st) {
     const int n_tiles = tile_rows * tiles_per_stripe(p.d);  // (tile_rows counts stripes)
     if (p.gbuf || p.gbuf_only || p.dbg_t || p.dbg_factor || p.phase_cycles)
         k_tile<true><<<n_tiles, kT, sizeof(TileSmem), st>>>(p);
+    else if (p.one_light_config)
+        return launch_tile_one_light(p, n_tiles, st);
     else
         k_tile<false><<<n_tiles, kT, sizeof(TileSmem), st>>>(p);
     return cudaGetLastError();
@@ -1153,7 +1197,7 @@ k_tile_order(const unsigned* __restrict__ cost, int* __restrict__ order, ViewDim
     const int stripe = max(d.stripe_n, 1);
     auto cost_of = [&](int t) {  // owned tile t (the CTA slot numbering of k_tile) -> its cost
         const int v = tile_row_first + (t / tps) * stripe;
-        return cost[(v / seg) * d.HW + (v % seg) * tps + t % tps];
+        return cost[(v / seg) * d.HW + stripe_column_segment(d, v) * tps + t % tps];
     };
     if (tid == 0) s_max = 1u;
     if (tid < kBuckets) s_hist[tid] = 0;
@@ -1190,3 +1234,4 @@ cudaError_t launch_tile_order(const unsigned* cost, int* order, const ViewDims& 
 }
 
 }  // namespace par
+#endif  // PAR_TILE_ONE_LIGHT

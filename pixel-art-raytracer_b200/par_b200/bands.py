@@ -57,13 +57,21 @@ def stripe_split_for(W: int, H: int, world: int) -> int:
     return 1
 
 
+def stripe_column_segment(v: int, world: int, split: int) -> int:
+    """Column segment of stripe v within its tile row v // split: v % split rotated by one for every
+    lcm(world, split) stripes, so that a rank's stripes visit all column segments in turn (v % world alone
+    gives a rank the same columns in every tile row when world and split share a factor); par_device.cuh."""
+    import math
+    return (v % split + v // math.lcm(world, split)) % split if split > 1 else 0
+
+
 def owned_rects(W: int, H: int, world: int, rank: int, split: int = 1) -> list[tuple[int, int, int, int]]:
     """(row0, row1, col0, col1) of the stripes rank `rank` renders with par_config.stripe_split = split."""
     split = max(split, 1)
     cols = (W // 40 // split) * 40
     out = []
     for v in range(rank, (H // 40) * split, world):
-        t, seg = divmod(v, split)
+        t, seg = v // split, stripe_column_segment(v, world, split)
         out.append((t * 40, t * 40 + 40, seg * cols, (seg + 1) * cols if split > 1 else W))
     return out
 

@@ -106,3 +106,8 @@ def test_split_stripes_partition(W, H, world):
         assert len(set(px)) == 1
     if (W, H, world) == (7680, 4320, 8):
         assert s == 2 and px[0] == W * H // 8
+    if s > 1:  # the column segments rotate: no rank renders only one side of the image
+        cols = (W // 40 // s) * 40
+        for r in range(world):
+            per_seg = [sum(1 for _, _, c0, _ in owned_rects(W, H, world, r, s) if c0 == k * cols) for k in range(s)]
+            assert max(per_seg) - min(per_seg) <= 1, (r, per_seg)

@@ -3,6 +3,8 @@ inputs) and against the reference's golden hashes.  Bar: bit-exact — grid cont
 entity ids, texel indices, world y/z, G-buffer bytes and final RGBA8 (SURVEY.md §8d
 "Tolerance": integer outputs and RGBA exact; fp32 intermediates are not exported, their
 0-ULP agreement is implied by exact RGBA on scenes with non-axis-aligned normals)."""
+import math
+
 import numpy as np
 import pytest
 
@@ -454,7 +456,7 @@ def test_split_stripes_reassemble(par, n, split, band):
     for i in range(n):
         m = np.zeros((H, W), bool)
         for v in range(i, (H // 40) * split, n):
-            t, sgm = divmod(v, split)
+            t, sgm = v // split, (v % split + v // math.lcm(n, split)) % split  # segments rotate: par_device.cuh
             m[t * 40:t * 40 + 40, sgm * tps * 40:(sgm + 1) * tps * 40] = True
         m[:a] = False
         m[b:] = False
@@ -1317,3 +1319,61 @@ def test_resident_flag_exchange_two_contexts_one_device(par, root, split):
             a.render_resident(lights)
             b.render_resident(lights)
         check("after an entity update")
+
+
+def _dense_scene(seed, W=1200, H=440, L=440, n=9000, n_lights=12):
+    from par_b200 import AABB, LIGHT
+    rng = np.random.default_rng(seed)
+    boxes = np.zeros(n, AABB)
+    boxes["px"] = rng.integers(0, W - 20, n)
+    boxes["py"] = rng.integers(0, 260, n)
+    boxes["pz"] = rng.integers(0, L - 20, n)
+    boxes["ex"] = boxes["ey"] = boxes["ez"] = 20
+    lights = np.zeros(n_lights, LIGHT)
+    lights["x"] = rng.integers(-2500, 4000, n_lights)
+    lights["y"] = rng.integers(20, 700, n_lights)
+    lights["z"] = rng.integers(-1500, 2500, n_lights)
+    k = min(4, n_lights)
+    lights["x"][:k] = rng.integers(0, W, k)  # some inside the view
+    lights["z"][:k] = rng.integers(0, L, k)
+    return boxes, lights
+
+
+@pytest.mark.parametrize("flags", ["256", "512"])
+@pytest.mark.parametrize("n_lights", [1, 12])
+def test_both_kernel_configurations_vs_oracle(par, oracle, monkeypatch, flags, n_lights):
+    """The render kernel is built twice (tile.cu / tile_one_light.cu: 5 CTAs per SM with large shared lists,
+    6 CTAs per SM with the smallest ones) and the library picks per frame (one light and many CTA waves ->
+    the second).  PAR_DEBUG_FLAGS 256 / 512 pin the first / second: a dense scene whose rounds overflow the
+    lists (re-walked, cut into step ranges) must give the oracle's frame on either, production frames
+    (no G-buffer checkpoint: that is the debug instantiation) and graph-replayed resident frames alike."""
+    W, H, L = 1200, 440, 440
+    boxes, lights = _dense_scene(21, W, H, L, n_lights=n_lights)
+    ref = oracle.render(W, H, L, boxes.view(oracle.AABB), lights.view(oracle.LIGHT), want_gbuf=False, want_texel=False)
+    monkeypatch.setenv("PAR_DEBUG_FLAGS", flags)
+    with par.Renderer(W, H, L) as r:
+        r.set_atlas()
+        r.set_scene(boxes)
+        rgba, _ = r.render(lights)
+        assert np.array_equal(_u32(rgba), _u32(ref["rgba"]))
+        for _ in range(3):
+            r.render_resident(lights)
+        got = r.read_frame()
+        r.sync()
+        assert np.array_equal(_u32(got), _u32(ref["rgba"]))
+
+
+@pytest.mark.parametrize("name", ["c2", "c3", "c5b"])
+def test_kernel_configurations_agree_at_full_size(par, oracle, workload_ops, monkeypatch, name):
+    """Full-size BASELINE frames on the pinned configurations (PAR_DEBUG_FLAGS 256 / 512) and on the automatic
+    choice: the committed oracle frame hash every time."""
+    g = workload_ops[name]
+    W, H, L = g["view"]
+    boxes, lights = _workload(par, name)
+    for flags in ("256", "512", "0"):
+        monkeypatch.setenv("PAR_DEBUG_FLAGS", flags)
+        with par.Renderer(W, H, L) as r:
+            r.set_atlas()
+            r.set_scene(boxes)
+            rgba, _ = r.render(lights)
+            assert "%016x" % oracle.fnv1a64(rgba) == g["frame_fnv1a64"], f"PAR_DEBUG_FLAGS={flags}"
