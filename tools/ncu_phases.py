@@ -45,7 +45,9 @@ def phase(f, l):
     return name
 
 
-out = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, "tile", "k_tile", "--symbol", sys.argv[2] if len(sys.argv) > 2 else "k_tileILb0", "--top", "2000", "--by", "inst"],
+# argv: report [mangled-name substring [cubin stem]] — e.g. k_tile_one_lightILb0 tile_one_light for the one-light build
+out = subprocess.run([sys.executable, "tools/ncu_lines.py", rep, sys.argv[3] if len(sys.argv) > 3 else "tile", "k_tile", "--symbol",
+                      sys.argv[2] if len(sys.argv) > 2 else "k_tileILb0", "--top", "2000", "--by", "inst"],
                      capture_output=True, text=True).stdout.splitlines()
 print(out[0])
 agg = {}

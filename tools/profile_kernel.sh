@@ -4,7 +4,8 @@
 # has exited 0 without ncu); step 2 runs anywhere (no GPU needed), against the SAME build.
 #
 #   gpurun --timeout 600 -- 'tools/profile_kernel.sh capture c2 k_tile r02_tile_c2'
-#   tools/profile_kernel.sh report r02_tile_c2 tile k_tile     # -> profiles/<tag>_lines.txt, _metrics.txt
+#   tools/profile_kernel.sh report r02_tile_c3 tile k_tile k_tileILb0     # -> profiles/<tag>_lines.txt, _metrics.txt
+#   tools/profile_kernel.sh report r02_tile_c2 tile_one_light k_tile k_tile_one_lightILb0   (one-light frames run that build)
 set -euo pipefail
 cmd=${1:?capture|report}
 case "$cmd" in
@@ -22,7 +23,7 @@ report)
     mkdir -p profiles
     {
         echo "# ${tag} — ${kernel}, ncu --set full"
-        python tools/ncu_phases.py "$rep" 2>/dev/null || true
+        python tools/ncu_phases.py "$rep" "${5:-$kernel}" "$stem" 2>/dev/null || true
         echo
         python tools/ncu_lines.py "$rep" "$stem" "$kernel" --symbol "${5:-$kernel}" --top 40 --by inst
     } > "profiles/${tag}_lines.txt"
