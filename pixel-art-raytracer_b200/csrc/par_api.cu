@@ -778,15 +778,16 @@ int par_update_entities(par_ctx* c, int first, int count, const par_aabb* aabbs,
 
 // ---- frame ---------------------------------------------------------------------------------------------
 // Which build of the render kernel a frame runs on (tile.cu): the one-light configuration (6 CTAs per SM, small
-// lists) for one-light frames of at least 4 waves of CTAs — below that the longer latency of a CTA with 64
-// registers costs more than the sixth CTA hides (1920x1080 = 1.75 waves: +1 %; 480x320: +8 %).
+// lists) for one-light frames of at least 3 waves of CTAs (3840x2160: 7 waves, -7 %; its half on each of 2 GPUs,
+// 3.5 waves: -6 %) — below that the longer latency of a CTA with 64 registers costs more than the sixth CTA
+// hides (1920x1080 = 1.75 waves: +1 %; 480x320: +8 %).
 // PAR_DEBUG_FLAGS 256: never, 512: always (the parity tests run many-light scenes on it).
 static bool want_one_light_config(const par_ctx* c, int n_lights) {
     if (c->debug_flags & 256) return false;
     if (c->debug_flags & 512) return true;
     int first, rows;
     owned_tile_rows(c->d, first, rows);
-    return n_lights == 1 && (long)rows * tiles_per_stripe(c->d) >= 4L * c->cta_slots;
+    return n_lights == 1 && (long)rows * tiles_per_stripe(c->d) >= 3L * c->cta_slots;
 }
 
 static void fill_tile_params(par_ctx* c, TileParams& tp, const par_light* lights, int n_lights, uchar4* d_out) {
