@@ -70,6 +70,15 @@ def main():
             rgba, gbuf, _ = r.render(l, want_gbuf=True)
         ref = O.render(W, H, L, a.view(O.AABB), l.view(O.LIGHT), atlas=atlas.view(O.SPRITE), sprite_ids=ids)
         ok = gbuf.tobytes() == ref["gbuf"].tobytes() and np.array_equal(rgba.view(np.uint32), ref["rgba"].view(np.uint32))
+        # production frames (no G-buffer checkpoint) on either build of the render kernel (tile.cu / tile_one_light.cu)
+        for flags in ("256", "512"):
+            os.environ["PAR_DEBUG_FLAGS"] = flags
+            with par.Renderer(W, H, L) as r:
+                r.set_atlas(atlas, par.default_palette())
+                r.set_scene(a, ids)
+                prod, _ = r.render(l)
+            ok = ok and np.array_equal(prod.view(np.uint32), ref["rgba"].view(np.uint32))
+        os.environ.pop("PAR_DEBUG_FLAGS", None)
         if not ok:
             bad += 1
             diff = np.argwhere(rgba.view(np.uint32) != ref["rgba"].view(np.uint32))

@@ -11,6 +11,7 @@ tail -5 gpurun_out/${tag}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${tag}_smoke.log 2>&1; echo "smoke rc=$?"
 timeout 600 python bench.py > gpurun_out/${tag}_bench_line.json 2> gpurun_out/${tag}_bench.err; echo "bench rc=$?"
 head -c 600 gpurun_out/${tag}_bench_line.json; echo
+timeout 200 python tests/fuzz_parity.py ${FUZZ:-150} 5000 > gpurun_out/${tag}_fuzz.log 2>&1; echo "fuzz rc=$?"; tail -2 gpurun_out/${tag}_fuzz.log
 for wl in c2 c3 c5b; do
     timeout 400 tools/profile_kernel.sh capture $wl k_tile ${tag}_tile_$wl > gpurun_out/${tag}_capture_$wl.log 2>&1; echo "capture $wl rc=$?"
 done
