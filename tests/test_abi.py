@@ -60,3 +60,16 @@ def test_product_never_touches_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "import oracle" not in text and \
                     "from oracle" not in text, os.path.join(dirpath, f)
+
+
+def test_both_builds_list_every_cuda_source():
+    """build_native.sh compiles csrc/*.cu by glob; the CMake build names its sources — every translation
+    unit (the render kernel is built twice: tile.cu and tile_one_light.cu) must be in both, and the shipped
+    library must hold both builds of the render kernel."""
+    csrc = os.path.join(ROOT, "pixel-art-raytracer_b200", "csrc")
+    cmake = open(os.path.join(ROOT, "CMakeLists.txt")).read()
+    for f in sorted(os.listdir(csrc)):
+        if f.endswith(".cu"):
+            assert f"csrc/{f}" in cmake, f"{f} missing from CMakeLists.txt"
+    so = open(os.path.join(ROOT, "pixel-art-raytracer_b200", "par_b200", "libpar_b200.so"), "rb").read()
+    assert b"k_tileILb0" in so and b"k_tile_one_lightILb0" in so
