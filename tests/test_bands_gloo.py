@@ -111,3 +111,35 @@ def test_split_stripes_partition(W, H, world):
         for r in range(world):
             per_seg = [sum(1 for _, _, c0, _ in owned_rects(W, H, world, r, s) if c0 == k * cols) for k in range(s)]
             assert max(per_seg) - min(per_seg) <= 1, (r, per_seg)
+
+
+@pytest.fixture(scope="module")
+def stripe_harness(tmp_path_factory):
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path_factory.mktemp("stripes") / "stripe_partition"
+    subprocess.run([nvcc, "-std=c++17", "-x", "cu", "-I", os.path.join(PKG, "csrc"), "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "stripe_partition.cpp"), "-o", str(exe)], check=True)
+    return str(exe)
+
+
+@pytest.mark.parametrize("W,H,world,split", [(7680, 4320, 8, 2), (3840, 2160, 8, 4), (3840, 2160, 4, 2), (640, 360, 3, 2),
+                                             (1280, 680, 2, 2), (1280, 720, 6, 4), (3840, 2160, 8, 8), (7680, 4320, 5, 1)])
+def test_device_stripe_arithmetic_equals_the_host_partition(stripe_harness, W, H, world, split):
+    """The stripe -> (tile row, column segment) arithmetic of the render kernel / C ABI (par_device.cuh, compiled
+    for the host) deals exactly the rectangles par_b200.bands.owned_rects states, rank by rank, and
+    stripe_of_segment (the cursor probe's inverse) undoes it."""
+    import subprocess
+    sys.path.insert(0, PKG)
+    from par_b200.bands import owned_rects
+    res = subprocess.run([stripe_harness, str(W), str(H), str(world), str(split)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout[-300:] + res.stderr
+    got = {}
+    for ln in res.stdout.splitlines():
+        r, *rect = map(int, ln.split())
+        got.setdefault(r, []).append(tuple(rect))
+    for r in range(world):
+        assert got.get(r, []) == owned_rects(W, H, world, r, split), f"rank {r}"
