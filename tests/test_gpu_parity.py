@@ -1,8 +1,8 @@
 """GPU parity: the CUDA path, called through the C ABI, against the oracle (same seeded
 inputs) and against the reference's golden hashes.  Bar: bit-exact — grid contents, hit
 entity ids, texel indices, world y/z, G-buffer bytes and final RGBA8 (SURVEY.md §8d
-"Tolerance": integer outputs and RGBA exact; fp32 intermediates are not exported, their
-0-ULP agreement is implied by exact RGBA on scenes with non-axis-aligned normals)."""
+"Tolerance": integer outputs and RGBA exact; the fp32 intermediates — light direction, Lambert
+term, acc + ambient — are exported by par_debug_intermediates and held to <= 1 ULP, measured 0)."""
 import math
 
 import numpy as np
