@@ -13,19 +13,23 @@
 // Frames after the first send only what moved (FrameRenderer::submit_frame_moved: the scripted keys move
 // entity 0, alternative.cpp:641-660); --full-upload re-sends the whole scene every frame instead, as the
 // reference re-bins it every frame (alternative.cpp:689-693).
-// --ppm-seq DIR writes every finished frame as DIR/frame_NNN.ppm (the frame sink after the path:
-// alternative.cpp:774-788 hands the same bytes to the display); --pitch BYTES renders into host frames
-// with that row pitch, the locked-texture contract of alternative.cpp:774-783.
+// Frame sink (the step after the path: alternative.cpp:774-788 hands the same bytes to the display, and the
+// reference's README shows them as gif.gif): --ppm-seq DIR / --png-seq DIR write every finished frame as
+// DIR/frame_NNN.ppm / .png, --gif FILE writes the whole sequence as one animated GIF (include/par/frame_sink.hpp);
+// --pitch BYTES renders into host frames with that row pitch, the locked-texture contract of
+// alternative.cpp:774-783.
 //
 //   par_headless [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm out.ppm] [--ppm-seq dir]
-//                [--pitch bytes] [--sync] [--full-upload] [--no-hash]
+//                [--png-seq dir] [--gif out.gif] [--pitch bytes] [--sync] [--full-upload] [--no-hash]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <string>
 #include <vector>
 
+#include "par/frame_sink.hpp"
 #include "par/reference_types.hpp"
 
 namespace {
@@ -58,6 +62,8 @@ int main(int argc, char** argv) {
     char script = 0;
     const char* ppm = nullptr;
     const char* ppm_seq = nullptr;
+    const char* png_seq = nullptr;
+    const char* gif_path = nullptr;
     size_t pitch = 0;
     bool sync = false, hash = true, full_upload = false;
     for (int i = 1; i < argc; i++) {
@@ -75,6 +81,10 @@ int main(int argc, char** argv) {
             ppm = argv[++i];
         } else if (!strcmp(argv[i], "--ppm-seq") && i + 1 < argc) {
             ppm_seq = argv[++i];
+        } else if (!strcmp(argv[i], "--png-seq") && i + 1 < argc) {
+            png_seq = argv[++i];
+        } else if (!strcmp(argv[i], "--gif") && i + 1 < argc) {
+            gif_path = argv[++i];
         } else if (!strcmp(argv[i], "--pitch") && i + 1 < argc) {
             pitch = static_cast<size_t>(atoll(argv[++i]));
         } else if (!strcmp(argv[i], "--full-upload")) {
@@ -85,7 +95,7 @@ int main(int argc, char** argv) {
             hash = false;
         } else {
             fprintf(stderr, "usage: %s [--view W H L] [--frames N] [--script C|D] [--device D] [--ppm f] [--ppm-seq dir] "
-                            "[--pitch bytes] [--sync] [--full-upload] [--no-hash]\n", argv[0]);
+                            "[--png-seq dir] [--gif f] [--pitch bytes] [--sync] [--full-upload] [--no-hash]\n", argv[0]);
             return 2;
         }
     }
@@ -113,20 +123,14 @@ int main(int argc, char** argv) {
         par::Color* texture[2] = {alloc_texture(), alloc_texture()};
         par::Color* last = texture[0];
         std::vector<par::Color> packed(pitch ? px : 0);  // pitched frames are packed for overlay / hash / PPM
-        auto write_ppm = [&](const char* path, const par::Color* frame) {
-            FILE* fp = fopen(path, "wb");
-            if (!fp) return false;
-            fprintf(fp, "P6\n%d %d\n255\n", W, H);
-            std::vector<unsigned char> rgb(px * 3);
-            for (size_t i = 0; i < px; i++) {
-                rgb[3 * i] = frame[i].red;
-                rgb[3 * i + 1] = frame[i].green;
-                rgb[3 * i + 2] = frame[i].blue;
-            }
-            fwrite(rgb.data(), 1, rgb.size(), fp);
-            fclose(fp);
-            return true;
+        auto write_ppm = [&](const char* path, const par::Color* frame) {  // (frames reach the sink packed)
+            return par::sink::write_ppm(path, frame, W, H, row_bytes);
         };
+        std::unique_ptr<par::sink::GifWriter> gif;
+        if (gif_path) {
+            gif.reset(new par::sink::GifWriter(gif_path, W, H));
+            if (!gif->ok()) throw par::Error(PAR_ERR_INVALID_ARG, "cannot write the --gif file");
+        }
         auto apply_script = [&](int f) {
             if (script == 'C' || script == 'D') {
                 par_aabb* player = reinterpret_cast<par_aabb*>(&entities.aabbs[0]);
@@ -149,6 +153,13 @@ int main(int argc, char** argv) {
                 snprintf(name, sizeof name, "/frame_%03d.ppm", f);
                 if (!write_ppm((std::string(ppm_seq) + name).c_str(), tex)) throw par::Error(PAR_ERR_INVALID_ARG, "cannot write into the --ppm-seq directory");
             }
+            if (png_seq) {
+                char name[32];
+                snprintf(name, sizeof name, "/frame_%03d.png", f);
+                if (!par::sink::write_png((std::string(png_seq) + name).c_str(), tex, W, H, row_bytes))
+                    throw par::Error(PAR_ERR_INVALID_ARG, "cannot write into the --png-seq directory");
+            }
+            if (gif && !gif->add_frame(tex, row_bytes)) throw par::Error(PAR_ERR_INVALID_ARG, "cannot write the --gif file");
             last = tex;
         };
         double gpu_ms = 0;
@@ -191,6 +202,7 @@ int main(int argc, char** argv) {
                 wall_ms / frames, hash ? ", FNV hash" : "", 1e3 * frames / wall_ms, gpu_ms / frames,
                 sync ? "on the GPU (loader + kernels)" : "submit -> frame on the host (latency)");
         if (ppm && !write_ppm(ppm, last)) return 1;
+        if (gif && !gif->close()) return 1;
         par_free_host(texture[0]);
         par_free_host(texture[1]);
     } catch (const par::Error& e) {

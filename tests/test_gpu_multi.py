@@ -202,6 +202,35 @@ def test_headless_driver_writes_the_frame_sequence(par, golden, tmp_path):
     assert len(seen) == n  # the player moves every frame
 
 
+def test_headless_driver_png_and_gif_sinks(par, golden, tmp_path):
+    """--png-seq / --gif (include/par/frame_sink.hpp, the writers are tested on the CPU by tests/test_frame_sink.py):
+    the PNG of every frame decodes to the bytes of its PPM, the animated GIF holds all frames (exact when a frame
+    has <= 256 colours, else within half a level of the 6x7x6 palette) — what gif.gif is to the reference."""
+    Image = pytest.importorskip("PIL.Image")
+    exe = os.path.join(PKG, "build", "par_headless")
+    if not os.path.exists(exe):
+        pytest.skip("par_headless not built")
+    W, H, n = 480, 320, 8
+    ppm_dir, png_dir, gif_path = tmp_path / "ppm", tmp_path / "png", tmp_path / "seq.gif"
+    ppm_dir.mkdir()
+    png_dir.mkdir()
+    out = subprocess.run([exe, "--frames", str(n), "--script", "C", "--ppm-seq", str(ppm_dir), "--png-seq", str(png_dir),
+                          "--gif", str(gif_path)], check=True, capture_output=True, text=True).stdout
+    assert [ln.split()[1] for ln in out.splitlines()] == golden["tier0_480x320x320_scriptC_240"]["fnv1a64"][:n]
+    gif = Image.open(gif_path)
+    assert gif.n_frames == n and gif.size == (W, H)
+    for f in range(n):
+        ppm = np.asarray(Image.open(ppm_dir / f"frame_{f:03d}.ppm").convert("RGB"))
+        png = np.asarray(Image.open(png_dir / f"frame_{f:03d}.png").convert("RGB"))
+        assert np.array_equal(png, ppm)
+        gif.seek(f)
+        got = np.asarray(gif.convert("RGB")).astype(int)
+        if len(np.unique(ppm.reshape(-1, 3), axis=0)) <= 256:
+            assert np.array_equal(got, ppm)
+        else:
+            assert np.abs(got - ppm.astype(int)).max() <= 26
+
+
 @pytest.mark.parametrize("root,split", [(-1, 1), (0, 1), (1, 1), (-1, 2), (0, 4)])
 def test_resident_frames_with_flag_exchange(par, root, split):
     """par_render_resident + par_exchange_setup on two GPUs: the render kernels store their stripes into the
