@@ -507,13 +507,31 @@ def c4_sequence(env, golden_sha):
                          "d2h_bytes_per_frame": W * H * 4 + 28,
                          "hash_file_sha256_equals_reference": sha == golden_sha}
     ok = all(m["hash_file_sha256_equals_reference"] for m in res.values())
+    # the same sequence driven by the compiled host (host/par_headless.cpp on par::FrameRenderer — the reference's
+    # main loop is C++ too): informational, its own wall clock, its own hash file
+    cpp = None
+    exe = os.path.join(PKG, "build", "par_headless")
+    if os.path.exists(exe):
+        try:
+            import re
+            args = [exe, "--view", str(W), str(H), str(L), "--frames", str(frames), "--script", "D", "--device", str(env["local"])]
+            subprocess.run(args + ["--no-hash"], check=True, capture_output=True, timeout=120)  # warm-up (module load, clocks)
+            fast = subprocess.run(args + ["--no-hash"], check=True, capture_output=True, text=True, timeout=120)
+            hashed = subprocess.run(args, check=True, capture_output=True, timeout=120)
+            m = re.search(r"= ([0-9.]+) frames/s", fast.stderr)
+            cpp = {"frames_per_s": float(m.group(1)) if m else None,
+                   "hash_file_sha256_equals_reference": hashlib.sha256(hashed.stdout).hexdigest() == golden_sha,
+                   "host": "par_headless (C++, par::FrameRenderer::submit_frame_moved / wait_frame, cursor probe, overlay), "
+                           "a separate process, wall clock of its frame loop with no warm-up pass (the first frames carry the graph captures)"}
+        except Exception as e:  # informational only
+            cpp = {"unavailable": str(e)[:160]}
     line = {"workload": "c4: 240 frames of key script D, default scene at 1920x1080 (player and light move)",
             "frames": frames, "frames_per_s": res["incremental_update"]["frames_per_s"],
             "ms_per_frame": res["incremental_update"]["ms_per_frame"], "modes": res,
             "timing": "wall clock of the host loop (scene update, submit, wait, cursor probe, overlay), two frames in "
                       "flight; hashes taken in a separate untimed pass",
             "api": {"incremental_update": "par_submit_update / par_wait_frame", "full_upload": "par_submit_frame / par_wait_frame"},
-            "reference_hash_file_sha256": golden_sha, "all_hash_files_equal_reference": ok}
+            "reference_hash_file_sha256": golden_sha, "all_hash_files_equal_reference": ok, "cpp_host": cpp}
     if not ok:
         raise SystemExit(f"bench.py: C4 sequence hashes differ from the reference's: {line}")
     return line
